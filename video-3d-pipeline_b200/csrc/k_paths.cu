@@ -1,0 +1,320 @@
+// Semi-global path aggregation and winner-takes-all.
+// Replaces the middle of cv2.StereoSGBM.compute (depth.py:341): OpenCV computeDisparitySGBM's
+// L_r recurrences, S = sum_r L_r, per-pixel argmin, uniqueness test and the S[best-1], S[best+1]
+// taps the sub-pixel step needs.  Spec: SURVEY.md Appendix A.3 / A.4.
+//
+// One WARP owns one path (a row for the horizontal directions, a wrapped column/diagonal for the
+// vertical ones) and walks it sequentially.  Lane l holds the 2*NR consecutive disparities
+// d = 2*NR*l .. 2*NR*l + 2*NR-1 as NR packed int16x2 registers, so one warp-step is one coalesced
+// 128*NR-byte load of C, the DPX packed min/add recurrence, one CREDUX warp-min and one
+// read-modify-write of S.
+//   state kept per path:  M[d] = min(L[d] - min_d L, P2)      (the P2 clamp folds the "minL + P2" term)
+//   step:                 L[d] = C[d] + min(M[d], min(M[d-1], M[d+1]) + P1)
+// A predecessor outside the window contributes L = 0, i.e. M = 0, which is also the initial state.
+#include "v3d_internal.h"
+
+namespace {
+
+template <int NR> struct Vec;
+template <> struct Vec<1> { using T = uint32_t; };
+template <> struct Vec<2> { using T = uint2; };
+template <> struct Vec<4> { using T = uint4; };
+
+template <int NR> __device__ __forceinline__ void unpack(const typename Vec<NR>::T& v, uint32_t (&r)[NR]);
+template <> __device__ __forceinline__ void unpack<1>(const uint32_t& v, uint32_t (&r)[1]) { r[0] = v; }
+template <> __device__ __forceinline__ void unpack<2>(const uint2& v, uint32_t (&r)[2]) { r[0] = v.x; r[1] = v.y; }
+template <> __device__ __forceinline__ void unpack<4>(const uint4& v, uint32_t (&r)[4]) { r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
+template <int NR> __device__ __forceinline__ typename Vec<NR>::T pack(const uint32_t (&r)[NR]);
+template <> __device__ __forceinline__ uint32_t pack<1>(const uint32_t (&r)[1]) { return r[0]; }
+template <> __device__ __forceinline__ uint2 pack<2>(const uint32_t (&r)[2]) { return make_uint2(r[0], r[1]); }
+template <> __device__ __forceinline__ uint4 pack<4>(const uint32_t (&r)[4]) { return make_uint4(r[0], r[1], r[2], r[3]); }
+
+// One step of the recurrence.  M in/out, C in, L out.  P1p / P2p are P1, P2 duplicated in both halves.
+template <int NR>
+__device__ __forceinline__ void path_step(uint32_t (&M)[NR], const uint32_t (&C)[NR], uint32_t (&L)[NR],
+                                          uint32_t P1p, uint32_t P2p, int lane)
+{
+    uint32_t up = __shfl_up_sync(V3D_FULL_MASK, M[NR - 1], 1);
+    uint32_t dn = __shfl_down_sync(V3D_FULL_MASK, M[0], 1);
+    // d = -1 and d = D do not exist: any value >= P2 is "infinity" because M <= P2 and P1 > 0
+    if (lane == 0) up = P2p;
+    if (lane == 31) dn = P2p;
+    uint32_t sh[NR + 1];
+    sh[0] = __byte_perm(up, M[0], 0x5432);            // (M[d-1] for the even d, M[d-1] for the odd d)
+#pragma unroll
+    for (int k = 1; k < NR; k++) sh[k] = __byte_perm(M[k - 1], M[k], 0x5432);
+    sh[NR] = __byte_perm(M[NR - 1], dn, 0x5432);
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+        const uint32_t nb = __vminu2(sh[k], sh[k + 1]);
+        L[k] = C[k] + __viaddmin_u16x2(nb, P1p, M[k]);   // halves never carry: C + P2 < 2^15
+        m = __vminu2(m, L[k]);
+    }
+    m = __vminu2(m, __byte_perm(m, 0, 0x1032));          // both halves = this lane's minimum
+    const uint32_t mm = __reduce_min_sync(V3D_FULL_MASK, m);
+    const uint32_t neg = ((0x10000u - (mm & 0xffffu)) & 0xffffu) * 0x10001u;
+#pragma unroll
+    for (int k = 0; k < NR; k++) M[k] = __viaddmin_s16x2(L[k], neg, P2p);
+}
+
+enum { S_WRITE = 0, S_ACCUM = 1 };
+
+// ------------------------------------------------------------------------------------------
+// Vertical / diagonal directions.  sx = x step along the path (-dx), sy = y step (-dy).
+// Warp k of a frame walks the path that is at column k in the first row; columns wrap, and a wrap
+// is a path start.
+// ------------------------------------------------------------------------------------------
+template <int NR, int SMODE, int PF>
+__global__ void __launch_bounds__(256)
+k_path_vert(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, int H, int sx, int sy,
+            uint32_t P1p, uint32_t P2p)
+{
+    using VT = typename Vec<NR>::T;
+    constexpr int D = 64 * NR;
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= W1) return;
+    const size_t frame = (size_t)blockIdx.y * H * W1;
+    const VT* C = reinterpret_cast<const VT*>(Cv) + frame * 32 + lane;
+    VT* S = reinterpret_cast<VT*>(Sv) + frame * 32 + lane;
+
+    int xp = k, yp = sy > 0 ? 0 : H - 1;                // prefetch cursor
+    VT cq[PF], sq[PF];
+#pragma unroll
+    for (int j = 0; j < PF; j++) {
+        if (j < H) {
+            const size_t o = ((size_t)yp * W1 + xp) * 32;
+            cq[j] = __ldg(C + o);
+            if (SMODE == S_ACCUM) sq[j] = S[o];
+            xp += sx; if (xp < 0) xp += W1; if (xp >= W1) xp -= W1;
+            yp += sy;
+        }
+    }
+    uint32_t M[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) M[r] = 0;
+    int x = k, y = sy > 0 ? 0 : H - 1;
+    for (int base = 0; base < H; base += PF) {
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            const int i = base + j;
+            if (i >= H) break;
+            uint32_t Cr[NR], Sr[NR], L[NR];
+            unpack<NR>(cq[j], Cr);
+            if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
+            if (i + PF < H) {
+                const size_t o = ((size_t)yp * W1 + xp) * 32;
+                cq[j] = __ldg(C + o);
+                if (SMODE == S_ACCUM) sq[j] = S[o];
+                xp += sx; if (xp < 0) xp += W1; if (xp >= W1) xp -= W1;
+                yp += sy;
+            }
+            path_step<NR>(M, Cr, L, P1p, P2p, lane);
+#pragma unroll
+            for (int r = 0; r < NR; r++) Sr[r] = (SMODE == S_ACCUM) ? Sr[r] + L[r] : L[r];
+            S[((size_t)y * W1 + x) * 32] = pack<NR>(Sr);
+            // advance; leaving the window on either side starts a new path at the far edge
+            x += sx; y += sy;
+            if (x < 0 || x >= W1) {
+                x = x < 0 ? x + W1 : x - W1;
+#pragma unroll
+                for (int r = 0; r < NR; r++) M[r] = 0;
+            }
+        }
+    }
+    (void)D;
+}
+
+// ------------------------------------------------------------------------------------------
+// Horizontal direction left -> right (predecessor x-1): one warp per row, accumulates into S.
+// ------------------------------------------------------------------------------------------
+template <int NR, int SMODE, int PF>
+__global__ void __launch_bounds__(256)
+k_path_lr(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, int rows,
+          uint32_t P1p, uint32_t P2p)
+{
+    using VT = typename Vec<NR>::T;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // row over all frames
+    if (row >= rows) return;
+    const VT* C = reinterpret_cast<const VT*>(Cv) + (size_t)row * W1 * 32 + lane;
+    VT* S = reinterpret_cast<VT*>(Sv) + (size_t)row * W1 * 32 + lane;
+    VT cq[PF], sq[PF];
+#pragma unroll
+    for (int j = 0; j < PF; j++)
+        if (j < W1) { cq[j] = __ldg(C + (size_t)j * 32); if (SMODE == S_ACCUM) sq[j] = S[(size_t)j * 32]; }
+    uint32_t M[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) M[r] = 0;
+    for (int base = 0; base < W1; base += PF) {
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            const int i = base + j;
+            if (i >= W1) break;
+            uint32_t Cr[NR], Sr[NR], L[NR];
+            unpack<NR>(cq[j], Cr);
+            if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
+            if (i + PF < W1) {
+                cq[j] = __ldg(C + (size_t)(i + PF) * 32);
+                if (SMODE == S_ACCUM) sq[j] = S[(size_t)(i + PF) * 32];
+            }
+            path_step<NR>(M, Cr, L, P1p, P2p, lane);
+#pragma unroll
+            for (int r = 0; r < NR; r++) Sr[r] = (SMODE == S_ACCUM) ? Sr[r] + L[r] : L[r];
+            S[(size_t)i * 32] = pack<NR>(Sr);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Horizontal direction right -> left (predecessor x+1) fused with winner-takes-all: the last
+// direction, so S_total = S + L never goes back to memory.  Per pixel it emits one 8-byte record
+//   .x = minS | best << 16      (best = 0xffff when the uniqueness test rejects the pixel)
+//   .y = S[best-1] | S[best+1] << 16
+// which k_select turns into the disparity (disp2 vote, sub-pixel, LR check).
+// ------------------------------------------------------------------------------------------
+template <int NR, int PF, bool TAP_S>
+__global__ void __launch_bounds__(256)
+k_path_rl_wta(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, uint2* __restrict__ rec, int W1,
+              int rows, uint32_t P1p, uint32_t P2p, int uniq)
+{
+    using VT = typename Vec<NR>::T;
+    constexpr int D = 64 * NR;
+    __shared__ uint32_t srow[8][2][D / 2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int row = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (row >= rows) return;
+    const VT* C = reinterpret_cast<const VT*>(Cv) + (size_t)row * W1 * 32 + lane;
+    VT* S = reinterpret_cast<VT*>(Sv) + (size_t)row * W1 * 32 + lane;
+    rec += (size_t)row * W1;
+
+    // per-lane constants: disparity indices of the 2*NR values this lane holds
+    uint32_t dc[NR], idx[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const uint32_t d0 = 2 * NR * lane + 2 * r;
+        dc[r] = d0 | ((d0 + 1) << 8);
+        idx[r] = d0 | ((d0 + 1) << 16);
+    }
+
+    VT cq[PF], sq[PF];
+#pragma unroll
+    for (int j = 0; j < PF; j++)
+        if (j < W1) { cq[j] = __ldg(C + (size_t)(W1 - 1 - j) * 32); sq[j] = S[(size_t)(W1 - 1 - j) * 32]; }
+    uint32_t M[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) M[r] = 0;
+    uint2 myrec = make_uint2(0, 0);
+    for (int base = 0; base < W1; base += PF) {
+#pragma unroll
+        for (int j = 0; j < PF; j++) {
+            const int i = base + j;
+            if (i >= W1) break;
+            const int x = W1 - 1 - i;
+            uint32_t Cr[NR], Sr[NR], L[NR];
+            unpack<NR>(cq[j], Cr);
+            unpack<NR>(sq[j], Sr);
+            if (i + PF < W1) {
+                cq[j] = __ldg(C + (size_t)(x - PF) * 32);
+                sq[j] = S[(size_t)(x - PF) * 32];
+            }
+            path_step<NR>(M, Cr, L, P1p, P2p, lane);
+#pragma unroll
+            for (int r = 0; r < NR; r++) Sr[r] += L[r];
+            if (TAP_S) S[(size_t)x * 32] = pack<NR>(Sr);
+
+            // ---- winner takes all: first argmin via (S << 8 | d) keys ----
+            uint32_t key = 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                key = min(key, __byte_perm(Sr[r], dc[r], 0x7104));
+                key = min(key, __byte_perm(Sr[r], dc[r], 0x7325));
+            }
+            key = __reduce_min_sync(V3D_FULL_MASK, key);
+            const uint32_t best = key & 0xffu, minS = key >> 8;
+            // ---- uniqueness: smallest S over |d - best| > 1 ----
+            const uint32_t off = ((1u - best) & 0xffffu) * 0x10001u;     // t = d - best + 1 in each half
+            uint32_t m2 = 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                const uint32_t t = __vadd2(idx[r], off);
+                const uint32_t e = __vadd2(__vminu2(t, 0x00030003u), 0xfffdfffdu);  // 0xfffd..0xffff iff t in {0,1,2}
+                m2 = __vminu2(m2, __vmaxu2(Sr[r], e));
+            }
+            m2 = __vminu2(m2, __byte_perm(m2, 0, 0x1032));
+            const uint32_t minS2 = __reduce_min_sync(V3D_FULL_MASK, m2) & 0xffffu;
+            const bool reject = minS2 * (uint32_t)(100 - uniq) < minS * 100u;
+            // ---- neighbours of the minimum, through a per-warp shared row ----
+            uint32_t* sr = srow[wib][i & 1];
+#pragma unroll
+            for (int r = 0; r < NR; r++) sr[lane * NR + r] = Sr[r];
+            __syncwarp();
+            const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sr);
+            const uint32_t sm1 = s16[best > 0 ? best - 1 : 0];
+            const uint32_t sp1 = s16[best < D - 1 ? best + 1 : D - 1];
+            if (lane == (i & 31)) {
+                myrec.x = (minS & 0xffffu) | ((reject ? 0xffffu : best) << 16);
+                myrec.y = sm1 | (sp1 << 16);
+            }
+            if ((i & 31) == 31 || i == W1 - 1) {
+                const int i0 = i & ~31;
+                if (i0 + lane <= i) rec[W1 - 1 - (i0 + lane)] = myrec;
+            }
+        }
+    }
+}
+
+template <int NR>
+int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
+{
+    constexpr int PF = NR == 4 ? 4 : 8;
+    const int W1 = ctx->W1, H = ctx->H;
+    const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
+    const uint16_t* C = ctx->C;
+    uint16_t* S = ctx->S;
+    const int wpb = 8;
+    dim3 block(wpb * 32);
+    dim3 gv((W1 + wpb - 1) / wpb, batch);
+    const int rows = batch * H;
+    dim3 gh((rows + wpb - 1) / wpb);
+    {
+        V3dScope scope(ctx, ST_PATHS, st);
+        // top-down sweep: predecessors (x, y-1), (x-1, y-1), (x+1, y-1)
+        k_path_vert<NR, S_WRITE, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, +1, P1p, P2p);
+        k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, +1, +1, P1p, P2p);
+        k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, -1, +1, P1p, P2p);
+        V3D_LAUNCHED(ctx, 3);
+        if (ctx->p.mode == V3D_MODE_HH) {
+            // bottom-up sweep: predecessors (x, y+1), (x+1, y+1), (x-1, y+1)
+            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, -1, P1p, P2p);
+            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, -1, -1, P1p, P2p);
+            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, +1, -1, P1p, P2p);
+            V3D_LAUNCHED(ctx, 3);
+        }
+        k_path_lr<NR, S_ACCUM, PF><<<gh, block, 0, st>>>(C, S, W1, rows, P1p, P2p);
+        V3D_LAUNCHED(ctx, 1);
+    }
+    {
+        V3dScope scope(ctx, ST_WTA, st);
+        if (tap_s)
+            k_path_rl_wta<NR, PF, true><<<gh, block, 0, st>>>(C, S, ctx->rec, W1, rows, P1p, P2p, ctx->uniq);
+        else
+            k_path_rl_wta<NR, PF, false><<<gh, block, 0, st>>>(C, S, ctx->rec, W1, rows, P1p, P2p, ctx->uniq);
+        V3D_LAUNCHED(ctx, 1);
+    }
+    return V3D_OK;
+}
+
+}  // namespace
+
+int v3d_launch_paths(v3d_ctx* ctx, int batch, cudaStream_t st)
+{
+    const bool tap_s = ctx->debug_taps != 0;   // parity tests ask the WTA pass to also store S_total
+    switch (ctx->D) {
+        case 64: return launch_paths_nr<1>(ctx, batch, st, tap_s);
+        case 128: return launch_paths_nr<2>(ctx, batch, st, tap_s);
+        case 256: return launch_paths_nr<4>(ctx, batch, st, tap_s);
+    }
+    return v3d_fail(V3D_EINVAL, "numDisparities %d unsupported (64, 128, 256)", ctx->D);
+}

@@ -1,0 +1,341 @@
+// Disparity selection (disp2 vote, sub-pixel, LR check), 3x3 median, speckle filter and the
+// reference's float / uint16 epilogue.
+// Replaces the tail of cv2.StereoSGBM.compute (depth.py:341: OpenCV computeDisparitySGBM's per-row
+// epilogue, medianBlur(disp, 3), filterSpeckles) and depth.py:341 (/16), :374 (<=0 -> 0), :400-403
+// (per-frame min-max -> uint16).  Spec: SURVEY.md Appendix A.4 - A.6.
+#include "v3d_internal.h"
+
+namespace {
+
+constexpr int INV = V3D_INVALID_DISP;
+
+// ---------------------------------------------------------------------------------------------
+// One block per image row.  cv2 walks x descending and keeps, for every right-image column x2, the
+// cheapest vote (strict '>' => among equal costs the largest x wins); atomicMin on
+// (minS << 16 | 0xffff - x) reproduces that independent of thread order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_select(const uint2* __restrict__ rec, int16_t* __restrict__ raw, int W, int W1, int D, int maxdiff)
+{
+    extern __shared__ uint32_t smem[];
+    uint32_t* key = smem;                                   // [W]
+    int16_t* d16row = reinterpret_cast<int16_t*>(smem + W); // [W]
+    const size_t row = blockIdx.x;
+    rec += row * W1;
+    raw += row * W;
+    for (int X = threadIdx.x; X < W; X += blockDim.x) { key[X] = 0xffffffffu; d16row[X] = (int16_t)INV; }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W1; x += blockDim.x) {
+        const uint2 r = __ldg(rec + x);
+        const uint32_t best = r.x >> 16;
+        if (best == 0xffffu) continue;                      // failed the uniqueness test
+        const int minS = (int)(r.x & 0xffffu);
+        atomicMin(&key[x + D - (int)best], ((uint32_t)minS << 16) | (0xffffu - (uint32_t)x));
+        int d16 = (int)best * 16;
+        if (best > 0 && (int)best < D - 1) {
+            const int sm1 = (int)(r.y & 0xffffu), sp1 = (int)(r.y >> 16);
+            const int den = max(sm1 + sp1 - 2 * minS, 1);
+            d16 += ((sm1 - sp1) * 16 + den) / (den * 2);    // C truncating division
+        }
+        d16row[x + D] = (int16_t)d16;
+    }
+    __syncthreads();
+    for (int X = threadIdx.x; X < W; X += blockDim.x) {
+        int d1 = d16row[X];
+        if (X >= D && d1 != INV) {
+            const int dl = d1 >> 4, dh = (d1 + 15) >> 4;
+            const int xl = X - dl, xh = X - dh;
+            bool bad = true;
+            {
+                bool t = false;
+                if (xl >= 0 && xl < W) {
+                    const uint32_t k = key[xl];
+                    if (k != 0xffffffffu) {
+                        const int d2 = (int)(0xffffu - (k & 0xffffu)) + D - xl;
+                        t = abs(d2 - dl) > maxdiff;
+                    }
+                }
+                bad = bad && t;
+            }
+            {
+                bool t = false;
+                if (xh >= 0 && xh < W) {
+                    const uint32_t k = key[xh];
+                    if (k != 0xffffffffu) {
+                        const int d2 = (int)(0xffffu - (k & 0xffffu)) + D - xh;
+                        t = abs(d2 - dh) > maxdiff;
+                    }
+                }
+                bad = bad && t;
+            }
+            if (bad) d1 = INV;
+        }
+        raw[X] = (int16_t)d1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 median, replicate border, invalid values take part (cv2.medianBlur on CV_16S).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(int& a, int& b) { const int t = min(a, b); b = max(a, b); a = t; }
+
+__global__ void __launch_bounds__(256)
+k_median3(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t dpitch_e, size_t dstride_e, int W, int H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    src += (size_t)b * W * H;
+    int v[9];
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+        const int16_t* r = src + (size_t)min(max(y + dy, 0), H - 1) * W;
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) v[(dy + 1) * 3 + dx + 1] = __ldg(r + min(max(x + dx, 0), W - 1));
+    }
+    // 19-exchange median-of-9 network
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+    cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]);
+    cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+    cswap(v[4], v[2]);
+    dst[(size_t)b * dstride_e + (size_t)y * dpitch_e + x] = (int16_t)v[4];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Speckle filter = connected components (4-neighbour, edge iff both valid and |a-b| <= maxDiff)
+// with a size threshold.  Lock-free union-find on pixel indices; component size counted at the
+// root with warp-aggregated atomics.  Order independent, like cv2.filterSpeckles.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int* L, int i)
+{
+    int p = L[i];
+    while (p != i) { i = p; p = L[i]; }
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(int* L, int a, int b)
+{
+    bool done;
+    do {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_init(int* __restrict__ L, int* __restrict__ sizes, int n_total)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_total) { L[i] = i; sizes[i] = 0; }
+}
+
+// labels are indices into the whole batch buffer (frame b occupies [b*n, (b+1)*n))
+__global__ void __launch_bounds__(256)
+k_ccl_merge(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
+            int W, int H, int maxDiff)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const int16_t* d = disp + (size_t)b * dstride_e;
+    const int v = d[(size_t)y * dpitch_e + x];
+    if (v == INV) return;
+    const int i = (b * H + y) * W + x;
+    if (x > 0) {
+        const int u = d[(size_t)y * dpitch_e + x - 1];
+        if (u != INV && abs(u - v) <= maxDiff) uf_union(L, i, i - 1);
+    }
+    if (y > 0) {
+        const int u = d[(size_t)(y - 1) * dpitch_e + x];
+        if (u != INV && abs(u - v) <= maxDiff) uf_union(L, i, i - W);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_count(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
+            int* __restrict__ sizes, int W, int H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    const bool in = x < W;
+    int root = -1;
+    if (in) {
+        const int v = disp[(size_t)b * dstride_e + (size_t)y * dpitch_e + x];
+        if (v != INV) {
+            const int i = (b * H + y) * W + x;
+            root = uf_find(L, i);
+            L[i] = root;                       // flatten (roots never change after the merge kernel)
+        }
+    }
+    // warp-aggregate: one atomic per distinct root per warp
+    const unsigned active = __ballot_sync(V3D_FULL_MASK, root >= 0);
+    if (root >= 0) {
+        const unsigned peers = __match_any_sync(active, root);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sizes[root], __popc(peers));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_apply(int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, const int* __restrict__ L,
+            const int* __restrict__ sizes, int W, int H, int maxSize, int newVal)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    int16_t* p = disp + (size_t)b * dstride_e + (size_t)y * dpitch_e + x;
+    if (*p == INV) return;
+    const int root = L[(b * H + y) * W + x];
+    if (sizes[root] <= maxSize) *p = (int16_t)newVal;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue.  float32(disp)/16 with <=0 -> 0 is max(disp,0)/16, exact, so the per-frame min/max of
+// the float map are the min/max of max(disp,0) taken in integers.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_minmax_init(int* mm, int batch)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch) { mm[2 * i] = 0x7fffffff; mm[2 * i + 1] = -0x7fffffff - 1; }
+}
+
+__global__ void __launch_bounds__(256)
+k_minmax(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int W, int H, int* __restrict__ mm)
+{
+    const int b = blockIdx.y;
+    const int16_t* d = disp + (size_t)b * dstride_e;
+    int lo = 0x7fffffff, hi = -0x7fffffff;
+    const int n = W * H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int y = i / W, x = i - y * W;
+        const int v = max((int)d[(size_t)y * dpitch_e + x], 0);
+        lo = min(lo, v); hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(V3D_FULL_MASK, lo);
+    hi = __reduce_max_sync(V3D_FULL_MASK, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[2 * b], lo); atomicMax(&mm[2 * b + 1], hi); }
+}
+
+__global__ void __launch_bounds__(256)
+k_epilogue(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int W, int H,
+           const int* __restrict__ mm, float* __restrict__ f32, uint16_t* __restrict__ u16)
+{
+    const int b = blockIdx.y;
+    const int n = W * H;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int y = i / W, x = i - y * W;
+    const int v = max((int)disp[(size_t)b * dstride_e + (size_t)y * dpitch_e + x], 0);
+    const float f = __fdiv_rn((float)v, 16.0f);
+    if (f32) f32[(size_t)b * n + i] = f;
+    if (u16) {
+        const float mn = __fdiv_rn((float)mm[2 * b], 16.0f), mx = __fdiv_rn((float)mm[2 * b + 1], 16.0f);
+        uint16_t o = 0;
+        if (mx > mn) {
+            // three separately rounded IEEE operations, like numpy (depth.py:401)
+            const float t = __fmul_rn(__fdiv_rn(__fsub_rn(f, mn), __fsub_rn(mx, mn)), 65535.0f);
+            o = (uint16_t)t;
+        }
+        u16[(size_t)b * n + i] = o;
+    }
+}
+
+// save_depth_map on an arbitrary float map (depth.py:397-403): per-frame min/max then the same three
+// rounded operations.  Floats are ordered through the usual sign-flip integer key.
+__device__ __forceinline__ int fkey(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float funkey(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__global__ void __launch_bounds__(256)
+k_minmax_f32(const float* __restrict__ in, size_t n, int* __restrict__ mm)
+{
+    const int b = blockIdx.y;
+    const float* d = in + (size_t)b * n;
+    int lo = 0x7fffffff, hi = -0x7fffffff - 1;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = fkey(d[i]);
+        lo = min(lo, k); hi = max(hi, k);
+    }
+    lo = __reduce_min_sync(V3D_FULL_MASK, lo);
+    hi = __reduce_max_sync(V3D_FULL_MASK, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[2 * b], lo); atomicMax(&mm[2 * b + 1], hi); }
+}
+
+__global__ void __launch_bounds__(256)
+k_normalize_f32(const float* __restrict__ in, size_t n, const int* __restrict__ mm, uint16_t* __restrict__ out)
+{
+    const int b = blockIdx.y;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float mn = funkey(mm[2 * b]), mx = funkey(mm[2 * b + 1]);
+    uint16_t o = 0;
+    if (mx > mn) o = (uint16_t)__fmul_rn(__fdiv_rn(__fsub_rn(in[(size_t)b * n + i], mn), __fsub_rn(mx, mn)), 65535.0f);
+    out[(size_t)b * n + i] = o;
+}
+
+}  // namespace
+
+int v3d_launch_normalize_f32(v3d_ctx* ctx, const float* in, size_t n, int batch, uint16_t* out, cudaStream_t st)
+{
+    V3dScope scope(ctx, ST_POST, st);
+    k_minmax_init<<<(batch + 255) / 256, 256, 0, st>>>(ctx->minmax, batch);
+    dim3 g(148 * 2, batch);
+    k_minmax_f32<<<g, 256, 0, st>>>(in, n, ctx->minmax);
+    dim3 grid((unsigned)((n + 255) / 256), batch);
+    k_normalize_f32<<<grid, 256, 0, st>>>(in, n, ctx->minmax, out);
+    V3D_LAUNCHED(ctx, 3);
+    return V3D_OK;
+}
+
+int v3d_launch_select(v3d_ctx* ctx, int batch, cudaStream_t st)
+{
+    V3dScope scope(ctx, ST_SELECT, st);
+    const size_t smem = (size_t)ctx->W * 4 + (size_t)ctx->W * 2 + 16;
+    k_select<<<batch * ctx->H, 256, smem, st>>>(ctx->rec, ctx->raw, ctx->W, ctx->W1, ctx->D, ctx->maxdiff);
+    V3D_LAUNCHED(ctx, 1);
+    return V3D_OK;
+}
+
+int v3d_launch_median(v3d_ctx* ctx, int batch, int16_t* dst, size_t dpitch, size_t dstride, cudaStream_t st)
+{
+    V3dScope scope(ctx, ST_MEDIAN, st);
+    dim3 grid((ctx->W + 255) / 256, ctx->H, batch);
+    k_median3<<<grid, 256, 0, st>>>(ctx->raw, dst, dpitch / 2, dstride / 2, ctx->W, ctx->H);
+    V3D_LAUNCHED(ctx, 1);
+    return V3D_OK;
+}
+
+int v3d_launch_speckle(v3d_ctx* ctx, int batch, int16_t* disp, size_t dpitch, size_t dstride, cudaStream_t st)
+{
+    if (ctx->p.speckleWindowSize <= 0) return V3D_OK;
+    V3dScope scope(ctx, ST_SPECKLE, st);
+    const int W = ctx->W, H = ctx->H;
+    const int n_total = batch * W * H;
+    const int maxDiff = 16 * ctx->p.speckleRange;
+    dim3 grid((W + 255) / 256, H, batch);
+    k_ccl_init<<<(n_total + 255) / 256, 256, 0, st>>>(ctx->labels, ctx->sizes, n_total);
+    k_ccl_merge<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff);
+    k_ccl_count<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H);
+    k_ccl_apply<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H,
+                                      ctx->p.speckleWindowSize, (ctx->p.minDisparity - 1) * 16);
+    V3D_LAUNCHED(ctx, 4);
+    return V3D_OK;
+}
+
+int v3d_launch_post(v3d_ctx* ctx, const int16_t* disp, size_t dpitch, size_t dstride, int batch,
+                    float* f32, uint16_t* u16, cudaStream_t st)
+{
+    V3dScope scope(ctx, ST_POST, st);
+    const int W = ctx->W, H = ctx->H, n = W * H;
+    if (u16) {
+        k_minmax_init<<<(batch + 255) / 256, 256, 0, st>>>(ctx->minmax, batch);
+        dim3 g(148 * 2, batch);
+        k_minmax<<<g, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax);
+        V3D_LAUNCHED(ctx, 2);
+    }
+    dim3 grid((n + 255) / 256, batch);
+    k_epilogue<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax, f32, u16);
+    V3D_LAUNCHED(ctx, 1);
+    return V3D_OK;
+}

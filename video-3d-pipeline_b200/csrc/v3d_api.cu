@@ -1,0 +1,403 @@
+// C ABI of libv3d.so (see include/v3d.h): context, workspace, argument checking, stage sequencing.
+#include "v3d_internal.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+namespace {
+thread_local char g_err[512] = "";
+const char* const kStageNames[ST_COUNT] = { "split_gray", "prefilter", "cost", "paths", "wta", "select",
+                                            "median", "speckle", "post", "guided", "copy" };
+}  // namespace
+
+int v3d_fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int v3d_cuda_check(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return V3D_OK;
+    return v3d_fail(V3D_ECUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+
+V3dScope::V3dScope(v3d_ctx* ctx, int stage, cudaStream_t st) : c(ctx), idx(-1), s(st)
+{
+    if (c->timing <= 0) return;
+    V3dTimedSpan sp;
+    sp.stage = stage;
+    if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return;
+    cudaEventRecord(sp.a, s);
+    c->spans.push_back(sp);
+    idx = (int)c->spans.size() - 1;
+}
+
+V3dScope::~V3dScope()
+{
+    if (idx >= 0) cudaEventRecord(c->spans[idx].b, s);
+}
+
+static void drain_spans(v3d_ctx* ctx)
+{
+    for (auto& sp : ctx->spans) {
+        cudaEventSynchronize(sp.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) ctx->stage_ms[sp.stage] += ms;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+}
+
+extern "C" {
+
+const char* v3d_version(void) { return "libv3d 0.1.0 (sm_100a)"; }
+const char* v3d_last_error(void) { return g_err; }
+
+void v3d_default_params(v3d_sgbm_params* p)
+{
+    if (!p) return;
+    // depth.py:315-325
+    p->minDisparity = 0;
+    p->numDisparities = 64;
+    p->blockSize = 5;
+    p->P1 = 8 * 3 * 5 * 5;
+    p->P2 = 32 * 3 * 5 * 5;
+    p->disp12MaxDiff = 1;
+    p->preFilterCap = 0;
+    p->uniquenessRatio = 10;
+    p->speckleWindowSize = 100;
+    p->speckleRange = 32;
+    p->mode = V3D_MODE_SGBM;
+}
+
+static void free_all(v3d_ctx* c)
+{
+    void* ptrs[] = { c->grayL, c->grayR, c->pfL, c->pfR, c->C, c->S, c->rec, c->raw, c->med, c->disp, c->labels,
+                     c->sizes, c->minmax, c->f32_tmp, c->u16_tmp, c->ab, c->in_dev, c->guide_dev, c->out_dev };
+    for (void* p : ptrs) if (p) cudaFree(p);
+}
+
+int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, int max_batch, v3d_ctx** out)
+{
+    if (!params || !out) return v3d_fail(V3D_EINVAL, "null argument");
+    *out = nullptr;
+    const v3d_sgbm_params& p = *params;
+    if (p.minDisparity != 0) return v3d_fail(V3D_EINVAL, "minDisparity must be 0 (depth.py:316)");
+    if (p.numDisparities != 64 && p.numDisparities != 128 && p.numDisparities != 256)
+        return v3d_fail(V3D_EINVAL, "numDisparities %d unsupported (64, 128, 256)", p.numDisparities);
+    if (p.blockSize < 1 || !(p.blockSize & 1) || p.blockSize > 7)
+        return v3d_fail(V3D_EINVAL, "blockSize %d unsupported (1, 3, 5, 7)", p.blockSize);
+    if (p.mode != V3D_MODE_SGBM && p.mode != V3D_MODE_HH)
+        return v3d_fail(V3D_EINVAL, "mode %d unsupported (0 = SGBM, 1 = HH)", p.mode);
+    if (eye_w <= 0 || eye_h <= 0 || max_batch <= 0) return v3d_fail(V3D_EINVAL, "bad size");
+    if (eye_w > 65535) return v3d_fail(V3D_EINVAL, "eye width %d too large", eye_w);
+    if (eye_w - p.numDisparities <= p.blockSize / 2)   // cv2.error in stereosgbm.cpp
+        return v3d_fail(V3D_EINVAL, "eye width %d too small for numDisparities %d (cv2 raises here)", eye_w,
+                        p.numDisparities);
+    if (p.preFilterCap < 0 || p.preFilterCap > 63) return v3d_fail(V3D_EINVAL, "preFilterCap out of range");
+    if (p.uniquenessRatio > 100) return v3d_fail(V3D_EINVAL, "uniquenessRatio out of range");
+    const int P1 = p.P1 > 0 ? p.P1 : 2;
+    const int P2 = std::max(p.P2 > 0 ? p.P2 : 5, P1 + 1);
+    const int ndirs = p.mode == V3D_MODE_HH ? 8 : 5;
+    const int ftzero = std::max(p.preFilterCap, 15) | 1;
+    // worst-case block cost: blockSize^2 * (2*ftzero + 255/4); packed int16 state needs headroom
+    const int cmax = p.blockSize * p.blockSize * (2 * ftzero + 63);
+    if (cmax + P2 + P1 > 32000 || (long)ndirs * (cmax + P2) > 65535)
+        return v3d_fail(V3D_EINVAL, "P1/P2 too large for the packed 16-bit path state (cmax %d)", cmax);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return v3d_fail(V3D_ECUDA, "no CUDA device: libv3d has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return v3d_fail(V3D_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    V3D_CUDA(cudaSetDevice(device));
+
+    v3d_ctx* c = new (std::nothrow) v3d_ctx();
+    if (!c) return v3d_fail(V3D_ENOMEM, "host allocation failed");
+    c->device = device; c->p = p;
+    c->W = eye_w; c->H = eye_h; c->D = p.numDisparities; c->W1 = eye_w - c->D; c->R = p.blockSize / 2;
+    c->max_batch = max_batch; c->ndirs = ndirs;
+    c->P1 = P1; c->P2 = P2;
+    c->uniq = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
+    c->maxdiff = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
+    c->ftzero = ftzero;
+    c->gpitch = ((size_t)eye_w + 127) / 128 * 128;
+    c->last_batch = 0;
+
+    const size_t B = (size_t)max_batch, npx = (size_t)eye_w * eye_h;
+    const size_t vol = B * (size_t)eye_h * c->W1 * c->D * sizeof(uint16_t);
+    struct { void** p; size_t n; } allocs[] = {
+        { (void**)&c->grayL, B * c->gpitch * eye_h }, { (void**)&c->grayR, B * c->gpitch * eye_h },
+        { (void**)&c->pfL, B * npx * sizeof(uint2) }, { (void**)&c->pfR, B * npx * sizeof(uint2) },
+        { (void**)&c->C, vol }, { (void**)&c->S, vol },
+        { (void**)&c->rec, B * (size_t)eye_h * c->W1 * sizeof(uint2) },
+        { (void**)&c->raw, B * npx * 2 }, { (void**)&c->med, B * npx * 2 }, { (void**)&c->disp, B * npx * 2 },
+        { (void**)&c->labels, B * npx * 4 }, { (void**)&c->sizes, B * npx * 4 },
+        { (void**)&c->minmax, B * 2 * sizeof(int) },
+        { (void**)&c->f32_tmp, B * npx * 4 }, { (void**)&c->u16_tmp, B * npx * 2 },
+    };
+    for (auto& a : allocs) {
+        cudaError_t e = cudaMalloc(a.p, a.n);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            free_all(c);
+            delete c;
+            return v3d_fail(V3D_ENOMEM, "workspace allocation of %zu bytes failed: %s", a.n, cudaGetErrorString(e));
+        }
+        c->bytes += a.n;
+    }
+    *out = c;
+    return V3D_OK;
+}
+
+int v3d_destroy(v3d_ctx* ctx)
+{
+    if (!ctx) return V3D_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    drain_spans(ctx);
+    free_all(ctx);
+    delete ctx;
+    return V3D_OK;
+}
+
+size_t v3d_workspace_bytes(const v3d_ctx* ctx) { return ctx ? ctx->bytes : 0; }
+unsigned long long v3d_launch_count(const v3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int v3d_set_debug_taps(v3d_ctx* ctx, int enabled)
+{
+    if (!ctx) return v3d_fail(V3D_EINVAL, "null context");
+    ctx->debug_taps = enabled != 0;
+    return V3D_OK;
+}
+
+int v3d_set_timing(v3d_ctx* ctx, int enabled)
+{
+    if (!ctx) return v3d_fail(V3D_EINVAL, "null context");
+    ctx->timing = enabled != 0;
+    return V3D_OK;
+}
+
+int v3d_reset_timing(v3d_ctx* ctx)
+{
+    if (!ctx) return v3d_fail(V3D_EINVAL, "null context");
+    drain_spans(ctx);
+    for (double& m : ctx->stage_ms) m = 0.0;
+    return V3D_OK;
+}
+
+double v3d_stage_ms(v3d_ctx* ctx, int stage, const char** name)
+{
+    if (!ctx || stage < 0 || stage >= ST_COUNT) return -1.0;
+    drain_spans(ctx);
+    if (name) *name = kStageNames[stage];
+    return ctx->stage_ms[stage];
+}
+
+static int check_batch(v3d_ctx* ctx, int batch)
+{
+    if (!ctx) return v3d_fail(V3D_EINVAL, "null context");
+    if (batch <= 0 || batch > ctx->max_batch)
+        return v3d_fail(V3D_EINVAL, "batch %d outside 1..%d", batch, ctx->max_batch);
+    V3D_CUDA(cudaSetDevice(ctx->device));
+    return V3D_OK;
+}
+
+int v3d_split_gray(v3d_ctx* ctx, const uint8_t* sbs_bgr, size_t sbs_pitch, size_t sbs_stride, int sbs_w, int h,
+                   int batch, int unsqueeze, uint8_t* left_gray, uint8_t* right_gray, size_t gray_pitch,
+                   size_t gray_stride, void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!sbs_bgr || !left_gray || !right_gray) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (sbs_w <= 0 || (sbs_w & 1)) return v3d_fail(V3D_EINVAL, "SBS frame width must be even");   // depth.py:254-255
+    const int half = sbs_w / 2;
+    const int eye_w = unsqueeze ? 2 * half : half;
+    if (h <= 0 || gray_pitch < (size_t)eye_w || sbs_pitch < (size_t)sbs_w * 3) return v3d_fail(V3D_EINVAL, "bad pitch");
+    return v3d_launch_eyes_to_gray(ctx, sbs_bgr, sbs_bgr + (size_t)half * 3, sbs_pitch, sbs_stride, half, h, batch,
+                                   unsqueeze, left_gray, right_gray, gray_pitch, gray_stride, (cudaStream_t)stream);
+}
+
+int v3d_bgr_to_gray(v3d_ctx* ctx, const uint8_t* bgr, size_t pitch, size_t stride, int w, int h, int batch,
+                    uint8_t* gray, size_t gray_pitch, size_t gray_stride, void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!bgr || !gray) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (w <= 0 || h <= 0 || gray_pitch < (size_t)w || pitch < (size_t)w * 3) return v3d_fail(V3D_EINVAL, "bad pitch");
+    return v3d_launch_eyes_to_gray(ctx, bgr, nullptr, pitch, stride, w, h, batch, 0, gray, nullptr, gray_pitch,
+                                   gray_stride, (cudaStream_t)stream);
+}
+
+int v3d_unsqueeze_bgr(int device, const uint8_t* bgr, size_t pitch, size_t stride, int w, int h, int batch,
+                      uint8_t* out, size_t out_pitch, size_t out_stride, void* stream)
+{
+    if (!bgr || !out) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (w <= 0 || h <= 0 || batch <= 0 || pitch < (size_t)w * 3 || out_pitch < (size_t)w * 6)
+        return v3d_fail(V3D_EINVAL, "bad size or pitch");
+    V3D_CUDA(cudaSetDevice(device));
+    return v3d_launch_unsqueeze_bgr(bgr, pitch, stride, w, h, batch, out, out_pitch, out_stride, (cudaStream_t)stream);
+}
+
+int v3d_normalize_u16(v3d_ctx* ctx, const float* depth_f32, size_t n, int batch, uint16_t* out_u16, void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!depth_f32 || !out_u16 || n == 0) return v3d_fail(V3D_EINVAL, "null buffer");
+    return v3d_launch_normalize_f32(ctx, depth_f32, n, batch, out_u16, (cudaStream_t)stream);
+}
+
+int v3d_sgbm_compute(v3d_ctx* ctx, const uint8_t* left_gray, const uint8_t* right_gray, size_t gray_pitch,
+                     size_t gray_stride, int batch, int16_t* disp, size_t disp_pitch, size_t disp_stride,
+                     void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!left_gray || !right_gray || !disp) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (gray_pitch < (size_t)ctx->W || disp_pitch < (size_t)ctx->W * 2 || (disp_pitch & 1) || (disp_stride & 1))
+        return v3d_fail(V3D_EINVAL, "bad pitch");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = v3d_launch_prefilter(ctx, left_gray, right_gray, gray_pitch, gray_stride, batch, st))) return rc;
+    if ((rc = v3d_launch_cost(ctx, batch, st))) return rc;
+    if ((rc = v3d_launch_paths(ctx, batch, st))) return rc;
+    if ((rc = v3d_launch_select(ctx, batch, st))) return rc;
+    if (ctx->debug_taps) {
+        // keep the pre-speckle median for tap 3
+        if ((rc = v3d_launch_median(ctx, batch, ctx->med, (size_t)ctx->W * 2, (size_t)ctx->W * ctx->H * 2, st))) return rc;
+    }
+    if ((rc = v3d_launch_median(ctx, batch, disp, disp_pitch, disp_stride, st))) return rc;
+    if ((rc = v3d_launch_speckle(ctx, batch, disp, disp_pitch, disp_stride, st))) return rc;
+    ctx->last_batch = batch;
+    return V3D_OK;
+}
+
+int v3d_debug_tap(v3d_ctx* ctx, int which, void** dev_ptr, size_t* bytes)
+{
+    if (!ctx || !dev_ptr || !bytes) return v3d_fail(V3D_EINVAL, "null argument");
+    if (ctx->last_batch <= 0) return v3d_fail(V3D_ESTATE, "no v3d_sgbm_compute call yet");
+    if (!ctx->debug_taps && (which == 1 || which == 3))
+        return v3d_fail(V3D_ESTATE, "tap %d needs v3d_set_debug_taps(ctx, 1) before the compute call", which);
+    const size_t B = (size_t)ctx->last_batch;
+    const size_t vol = B * (size_t)ctx->H * ctx->W1 * ctx->D * sizeof(uint16_t);
+    const size_t img = B * (size_t)ctx->W * ctx->H * sizeof(int16_t);
+    switch (which) {
+        case 0: *dev_ptr = ctx->C; *bytes = vol; return V3D_OK;
+        case 1: *dev_ptr = ctx->S; *bytes = vol; return V3D_OK;
+        case 2: *dev_ptr = ctx->raw; *bytes = img; return V3D_OK;
+        case 3: *dev_ptr = ctx->med; *bytes = img; return V3D_OK;
+    }
+    return v3d_fail(V3D_EINVAL, "unknown tap %d", which);
+}
+
+int v3d_debug_tap_copy(v3d_ctx* ctx, int which, void* dst_dev, size_t dst_bytes, void* stream)
+{
+    void* src = nullptr;
+    size_t n = 0;
+    if (int rc = v3d_debug_tap(ctx, which, &src, &n)) return rc;
+    if (!dst_dev || dst_bytes < n) return v3d_fail(V3D_EINVAL, "tap %d needs %zu bytes", which, n);
+    V3D_CUDA(cudaMemcpyAsync(dst_dev, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return V3D_OK;
+}
+
+int v3d_postprocess(v3d_ctx* ctx, const int16_t* disp, size_t disp_pitch, size_t disp_stride, int batch,
+                    float* depth_f32, uint16_t* depth_u16, void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!disp) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (disp_pitch < (size_t)ctx->W * 2 || (disp_pitch & 1) || (disp_stride & 1)) return v3d_fail(V3D_EINVAL, "bad pitch");
+    if (!depth_f32 && !depth_u16) return V3D_OK;
+    return v3d_launch_post(ctx, disp, disp_pitch, disp_stride, batch, depth_f32, depth_u16, (cudaStream_t)stream);
+}
+
+int v3d_guided_upscale(v3d_ctx* ctx, const uint16_t* depth_u16, int w, int h, const uint8_t* guide_rgb, int gw,
+                       int gh, int batch, int r, float eps, uint16_t* out_u16, float* q_f32, void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!depth_u16 || !guide_rgb || !out_u16) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (w <= 0 || h <= 0 || gw <= 0 || gh <= 0 || gw > 32768 || gh > 32768 || w > 32768 || h > 32768)
+        return v3d_fail(V3D_EINVAL, "bad size");
+    if (!(eps > 0.f)) return v3d_fail(V3D_EINVAL, "eps must be positive");
+    return v3d_launch_guided(ctx, depth_u16, w, h, guide_rgb, gw, gh, batch, r, eps, out_u16, q_f32,
+                             (cudaStream_t)stream);
+}
+
+int v3d_depth_frames(v3d_ctx* ctx, const uint8_t* sbs_bgr, size_t sbs_pitch, size_t sbs_stride, int sbs_w, int h,
+                     int batch, int unsqueeze, int16_t* disp, float* depth_f32, uint16_t* depth_u16,
+                     const uint8_t* guide_rgb, int gw, int gh, int r, float eps, uint16_t* out_4k, void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (sbs_w <= 0 || (sbs_w & 1)) return v3d_fail(V3D_EINVAL, "SBS frame width must be even");
+    const int eye_w = unsqueeze ? sbs_w : sbs_w / 2;
+    if (eye_w != ctx->W || h != ctx->H)
+        return v3d_fail(V3D_EINVAL, "frame gives %dx%d eyes, context was created for %dx%d", eye_w, h, ctx->W, ctx->H);
+    if (guide_rgb && !out_4k) return v3d_fail(V3D_EINVAL, "guide given without an output buffer");
+    const size_t gstride = ctx->gpitch * ctx->H;
+    const size_t dpitch = (size_t)ctx->W * 2, dstride = dpitch * ctx->H;
+    int16_t* d = disp ? disp : ctx->disp;
+    int rc;
+    if ((rc = v3d_split_gray(ctx, sbs_bgr, sbs_pitch, sbs_stride, sbs_w, h, batch, unsqueeze, ctx->grayL, ctx->grayR,
+                             ctx->gpitch, gstride, stream))) return rc;
+    if ((rc = v3d_sgbm_compute(ctx, ctx->grayL, ctx->grayR, ctx->gpitch, gstride, batch, d, dpitch, dstride, stream)))
+        return rc;
+    uint16_t* u16 = depth_u16 ? depth_u16 : (guide_rgb ? ctx->u16_tmp : nullptr);
+    if ((rc = v3d_postprocess(ctx, d, dpitch, dstride, batch, depth_f32, u16, stream))) return rc;
+    if (guide_rgb)
+        if ((rc = v3d_guided_upscale(ctx, u16, ctx->W, ctx->H, guide_rgb, gw, gh, batch, r, eps, out_4k, nullptr,
+                                     stream))) return rc;
+    return V3D_OK;
+}
+
+static int ensure(v3d_ctx* ctx, void** p, size_t* have, size_t need)
+{
+    if (*have >= need) return V3D_OK;
+    if (*p) { V3D_CUDA(cudaDeviceSynchronize()); V3D_CUDA(cudaFree(*p)); ctx->bytes -= *have; *p = nullptr; *have = 0; }
+    V3D_CUDA(cudaMalloc(p, need));
+    *have = need; ctx->bytes += need;
+    return V3D_OK;
+}
+
+int v3d_depth_frames_host(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, int h, int batch, int unsqueeze,
+                          int16_t* disp_host, float* depth_f32_host, uint16_t* depth_u16_host,
+                          const uint8_t* guide_rgb_host, int gw, int gh, int r, float eps, uint16_t* out_4k_host,
+                          void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!sbs_bgr_host) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (guide_rgb_host && !out_4k_host) return v3d_fail(V3D_EINVAL, "guide given without an output buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t frame = (size_t)sbs_w * h * 3, npx = (size_t)ctx->W * ctx->H;
+    int rc;
+    if ((rc = ensure(ctx, (void**)&ctx->in_dev, &ctx->in_bytes, frame * batch))) return rc;
+    {
+        V3dScope scope(ctx, ST_COPY, st);
+        V3D_CUDA(cudaMemcpyAsync(ctx->in_dev, sbs_bgr_host, frame * batch, cudaMemcpyHostToDevice, st));
+        if (guide_rgb_host) {
+            const size_t gbytes = (size_t)gw * gh * 3 * batch;
+            if ((rc = ensure(ctx, (void**)&ctx->guide_dev, &ctx->guide_bytes, gbytes))) return rc;
+            if ((rc = ensure(ctx, (void**)&ctx->out_dev, &ctx->out_bytes, (size_t)gw * gh * 2 * batch))) return rc;
+            V3D_CUDA(cudaMemcpyAsync(ctx->guide_dev, guide_rgb_host, gbytes, cudaMemcpyHostToDevice, st));
+        }
+    }
+    rc = v3d_depth_frames(ctx, ctx->in_dev, (size_t)sbs_w * 3, frame, sbs_w, h, batch, unsqueeze, ctx->disp,
+                          depth_f32_host ? ctx->f32_tmp : nullptr, depth_u16_host || guide_rgb_host ? ctx->u16_tmp : nullptr,
+                          guide_rgb_host ? ctx->guide_dev : nullptr, gw, gh, r, eps,
+                          guide_rgb_host ? ctx->out_dev : nullptr, stream);
+    if (rc) return rc;
+    {
+        V3dScope scope(ctx, ST_COPY, st);
+        if (disp_host) V3D_CUDA(cudaMemcpyAsync(disp_host, ctx->disp, npx * 2 * batch, cudaMemcpyDeviceToHost, st));
+        if (depth_f32_host) V3D_CUDA(cudaMemcpyAsync(depth_f32_host, ctx->f32_tmp, npx * 4 * batch, cudaMemcpyDeviceToHost, st));
+        if (depth_u16_host) V3D_CUDA(cudaMemcpyAsync(depth_u16_host, ctx->u16_tmp, npx * 2 * batch, cudaMemcpyDeviceToHost, st));
+        if (out_4k_host) V3D_CUDA(cudaMemcpyAsync(out_4k_host, ctx->out_dev, (size_t)gw * gh * 2 * batch, cudaMemcpyDeviceToHost, st));
+    }
+    V3D_CUDA(cudaStreamSynchronize(st));
+    return V3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Internal declarations shared by the libv3d translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+#include "../../include/v3d.h"
+
+#define V3D_FULL_MASK 0xffffffffu
+
+enum V3dStage {
+    ST_SPLIT_GRAY = 0, ST_PREFILTER, ST_COST, ST_PATHS, ST_WTA, ST_SELECT, ST_MEDIAN,
+    ST_SPECKLE, ST_POST, ST_GUIDED, ST_COPY, ST_COUNT
+};
+
+struct V3dTimedSpan { int stage; cudaEvent_t a, b; };
+
+struct v3d_ctx {
+    int device;
+    v3d_sgbm_params p;
+    int W, H, D, W1, R, max_batch, ndirs;
+    int P1, P2, uniq, maxdiff, ftzero;
+
+    // workspace (device)
+    uint8_t *grayL, *grayR;      // [B][H][gpitch]
+    size_t gpitch;
+    uint2 *pfL, *pfR;            // prefilter records [B][H][W]: {sobel v,lo,hi,0 | intensity v,lo,hi,0}
+    uint16_t *C, *S;             // [B][H][W1][D]
+    uint2* rec;                  // WTA records [B][H][W1]
+    int16_t *raw, *med, *disp;   // [B][H][W]
+    int *labels, *sizes;         // [B][H*W]
+    int* minmax;                 // [B][2]
+    float* f32_tmp;              // [B][H][W]
+    uint16_t* u16_tmp;           // [B][H][W]
+    // lazily sized buffers
+    float4* ab; size_t ab_bytes;           // guided coefficients [B][gh][gw]
+    uint8_t* in_dev; size_t in_bytes;      // host-API staging: SBS frames
+    uint8_t* guide_dev; size_t guide_bytes;
+    uint16_t* out_dev; size_t out_bytes;
+    size_t bytes;
+    int last_batch;
+
+    unsigned long long launches;
+    int timing;
+    int debug_taps;          // keep S_total and the pre-speckle median for v3d_debug_tap
+    int guided_attr_set;
+    std::vector<V3dTimedSpan> spans;
+    double stage_ms[ST_COUNT];
+};
+
+// error plumbing (v3d_api.cu)
+int v3d_fail(int code, const char* fmt, ...);
+int v3d_cuda_check(cudaError_t e, const char* what);
+#define V3D_CUDA(x) do { int _rc = v3d_cuda_check((x), #x); if (_rc) return _rc; } while (0)
+#define V3D_LAUNCHED(ctx, n) do { (ctx)->launches += (n); int _rc = v3d_cuda_check(cudaGetLastError(), "kernel launch"); if (_rc) return _rc; } while (0)
+
+struct V3dScope {   // per-stage CUDA-event timing when ctx->timing is on
+    v3d_ctx* c; int idx; cudaStream_t s;
+    V3dScope(v3d_ctx* ctx, int stage, cudaStream_t st);
+    ~V3dScope();
+};
+
+// k_gray.cu
+int v3d_launch_eyes_to_gray(v3d_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, size_t pitch,
+                            size_t stride, int src_w, int h, int batch, int unsqueeze,
+                            uint8_t* left_gray, uint8_t* right_gray, size_t gpitch, size_t gstride,
+                            cudaStream_t st);
+int v3d_launch_unsqueeze_bgr(const uint8_t* src, size_t pitch, size_t stride, int w, int h, int batch,
+                             uint8_t* dst, size_t dpitch, size_t dstride, cudaStream_t st);
+// k_cost.cu
+int v3d_launch_prefilter(v3d_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t gpitch,
+                         size_t gstride, int batch, cudaStream_t st);
+int v3d_launch_cost(v3d_ctx* ctx, int batch, cudaStream_t st);
+// k_paths.cu
+int v3d_launch_paths(v3d_ctx* ctx, int batch, cudaStream_t st);
+// k_post.cu
+int v3d_launch_select(v3d_ctx* ctx, int batch, cudaStream_t st);
+int v3d_launch_median(v3d_ctx* ctx, int batch, int16_t* dst, size_t dpitch, size_t dstride, cudaStream_t st);
+int v3d_launch_speckle(v3d_ctx* ctx, int batch, int16_t* disp, size_t dpitch, size_t dstride, cudaStream_t st);
+int v3d_launch_post(v3d_ctx* ctx, const int16_t* disp, size_t dpitch, size_t dstride, int batch,
+                    float* f32, uint16_t* u16, cudaStream_t st);
+int v3d_launch_normalize_f32(v3d_ctx* ctx, const float* in, size_t n, int batch, uint16_t* out, cudaStream_t st);
+// k_guided.cu
+int v3d_launch_guided(v3d_ctx* ctx, const uint16_t* depth, int w, int h, const uint8_t* guide, int gw, int gh,
+                      int batch, int r, float eps, uint16_t* out, float* q, cudaStream_t st);
