@@ -88,3 +88,42 @@ def guided_upscale(depth_u16, guide_rgb, r=8, eps=1e-3):
     q = sum(box_mean(a[..., c], r) * I[..., c] for c in range(3)) + box_mean(b, r)
     out = np.floor(np.clip(q, 0.0, 1.0) * 65535.0 + 0.5).astype(np.uint16)
     return q, out
+
+
+def guided_upscale_cv2(depth_u16, guide_rgb, r=8, eps=1e-3):
+    """Fast CPU port of the same filter (fp32, cv2.resize + cv2.boxFilter).  Used ONLY as the timed
+    CPU baseline in bench.py; tests check it against guided_upscale() above."""
+    import cv2
+    guide_rgb = np.asarray(guide_rgb)
+    H, W = guide_rgb.shape[:2]
+    k = (2 * r + 1, 2 * r + 1)
+
+    def box(a):
+        return cv2.boxFilter(a, cv2.CV_32F, k, borderType=cv2.BORDER_REFLECT)
+
+    p = cv2.resize(np.asarray(depth_u16, np.float32) * np.float32(1.0 / 65535.0), (W, H), interpolation=cv2.INTER_LINEAR)
+    I = guide_rgb.astype(np.float32) * np.float32(1.0 / 255.0)
+    # centre the guide and the input about their global means (box sums are shift covariant)
+    I = I - I.reshape(-1, 3).mean(axis=0).astype(np.float32)
+    p0 = np.float32(p.mean())
+    p = p - p0
+    Ic = [np.ascontiguousarray(I[..., c]) for c in range(3)]
+    mI = [box(c) for c in Ic]
+    mp = box(p)
+    cov = [box(Ic[c] * p) - mI[c] * mp for c in range(3)]
+    var = {(i, j): box(Ic[i] * Ic[j]) - mI[i] * mI[j] for i in range(3) for j in range(i, 3)}
+    s00, s01, s02 = var[(0, 0)] + eps, var[(0, 1)], var[(0, 2)]
+    s11, s12, s22 = var[(1, 1)] + eps, var[(1, 2)], var[(2, 2)] + eps
+    c00 = s11 * s22 - s12 * s12
+    c01 = s02 * s12 - s01 * s22
+    c02 = s01 * s12 - s02 * s11
+    c11 = s00 * s22 - s02 * s02
+    c12 = s01 * s02 - s00 * s12
+    c22 = s00 * s11 - s01 * s01
+    det = s00 * c00 + s01 * c01 + s02 * c02
+    a0 = (c00 * cov[0] + c01 * cov[1] + c02 * cov[2]) / det
+    a1 = (c01 * cov[0] + c11 * cov[1] + c12 * cov[2]) / det
+    a2 = (c02 * cov[0] + c12 * cov[1] + c22 * cov[2]) / det
+    b = mp - a0 * mI[0] - a1 * mI[1] - a2 * mI[2]
+    q = box(a0) * Ic[0] + box(a1) * Ic[1] + box(a2) * Ic[2] + box(b) + p0
+    return q, np.floor(np.clip(q, 0.0, 1.0) * 65535.0 + 0.5).astype(np.uint16)

@@ -1,0 +1,205 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/v3d.h declares, the
+error paths that need no GPU behave, and the host-side logic (module surface, cache keys, frame
+sharding incl. a world_size-2 gloo run) is right."""
+import ctypes as C
+import hashlib
+import os
+import re
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "v3d.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(v3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from video_3d_pipeline import _native
+    lib = _native.lib()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"libv3d.so does not export {n}"
+    assert b"sm_100a" in lib.v3d_version()
+
+
+def test_params_struct_matches_header_and_reference_literals():
+    from video_3d_pipeline import _native
+    p = _native.SgbmParams()
+    _native.lib().v3d_default_params(C.byref(p))
+    # depth.py:315-325
+    assert (p.minDisparity, p.numDisparities, p.blockSize, p.P1, p.P2) == (0, 64, 5, 600, 2400)
+    assert (p.disp12MaxDiff, p.uniquenessRatio, p.speckleWindowSize, p.speckleRange, p.mode) == (1, 10, 100, 32, 0)
+    assert C.sizeof(p) == 44
+
+
+def test_create_validates_before_touching_cuda():
+    from video_3d_pipeline import _native
+    L = _native.lib()
+    h = C.c_void_p()
+    bad = [
+        (_native.SgbmParams(numDisparities=64), 66, 20),        # W - D <= blockSize/2 : cv2.error site
+        (_native.SgbmParams(numDisparities=48), 400, 20),       # unsupported D
+        (_native.SgbmParams(minDisparity=1), 400, 20),
+        (_native.SgbmParams(blockSize=4), 400, 20),
+        (_native.SgbmParams(mode=2), 400, 20),
+        (_native.SgbmParams(P2=60000), 400, 20),                # packed 16-bit state would overflow
+    ]
+    for p, w, hh in bad:
+        assert L.v3d_create(0, C.byref(p), w, hh, 1, C.byref(h)) == _native.V3D_EINVAL
+        assert L.v3d_last_error()
+    assert L.v3d_create(0, None, 400, 20, 1, C.byref(h)) == _native.V3D_EINVAL
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from video_3d_pipeline import _native
+    h = C.c_void_p()
+    p = _native.SgbmParams()
+    assert _native.lib().v3d_create(0, C.byref(p), 400, 20, 1, C.byref(h)) == _native.V3D_ECUDA
+    assert b"no CPU fallback" in _native.lib().v3d_last_error()
+    with pytest.raises(RuntimeError):
+        _native.Context(400, 20)
+    from video_3d_pipeline.depth import IGEVStereoDepthExtractor
+    with pytest.raises(RuntimeError, match="CUDA not available"):
+        IGEVStereoDepthExtractor(work_dir="/tmp/v3d_t", cache_dir="/tmp/v3d_t")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / "video-3d-pipeline_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")):
+        text = f.read_text()
+        assert "oracle" not in re.sub(r"#.*|//.*|\"\"\".*?\"\"\"", "", text, flags=re.S).replace("oracle/guided.py", ""), f
+    assert not re.search(r"^\s*(from|import)\s+oracle", (pkg / "video_3d_pipeline" / "_native.py").read_text(), re.M)
+
+
+def test_module_surface_matches_reference():
+    import video_3d_pipeline as v
+    from video_3d_pipeline import depth, upscale, utils
+    # reference __init__.py:5-16 + the name run_pipeline.py:12 imports
+    for n in ("VideoAligner", "IGEVStereoDepthExtractor", "SimpleDepthUpscaler", "get_video_info", "extract_audio",
+              "verify_video_compatibility"):
+        assert hasattr(v, n)
+    assert depth.IGEVStereoDepthExtractor is depth.HybridStereoDepthExtractor
+    import inspect
+    sig = inspect.signature(depth.HybridStereoDepthExtractor.__init__)
+    want = ["model_checkpoint", "work_dir", "cache_dir", "device", "batch_size", "use_neural_guidance", "stereo_only",
+            "unsqueeze_sbs"]                                             # depth.py:23-31, same order
+    assert list(sig.parameters)[1:1 + len(want)] == want
+    assert sig.parameters["batch_size"].default == 8 and sig.parameters["unsqueeze_sbs"].default is True
+    for m in ("load_model", "get_cache_path", "is_cached", "extract_frames_opencv", "extract_frames_ffmpeg",
+              "split_sbs_frame", "preprocess_frame_pair", "process_frame_batch", "save_depth_map", "process_video_sbs"):
+        assert callable(getattr(depth.HybridStereoDepthExtractor, m))
+    s = inspect.signature(depth.HybridStereoDepthExtractor.process_video_sbs)
+    assert list(s.parameters)[1:] == ["video_path", "start_frame", "max_frames", "force_reprocess"]
+    u = inspect.signature(upscale.SimpleDepthUpscaler.process_depth_upscaling)
+    assert list(u.parameters)[1:] == ["depth_dir", "video_4k_path", "output_path", "force_reprocess"]
+    assert list(inspect.signature(upscale.SimpleDepthUpscaler.upscale_depth_maps_ffmpeg).parameters)[1:6] == \
+        ["depth_dir", "target_width", "target_height", "output_path", "fps"]
+    assert callable(depth.main) and callable(upscale.main) and callable(utils.create_work_directory)
+
+
+def test_cache_key_is_the_references(tmp_path):
+    # depth.py:116-125: md5(f"{video}_{start}_{count}_{model}_{unsqueeze}")[:16]
+    from video_3d_pipeline.depth import HybridStereoDepthExtractor as E
+    ex = E.__new__(E)
+    ex.cache_dir = tmp_path
+    ex.model_checkpoint = "Intel/dpt-large"
+    ex.unsqueeze_sbs = True
+    p = ex.get_cache_path("clip.mkv", 5, 100)
+    key = hashlib.md5("clip.mkv_5_100_Intel/dpt-large_True".encode()).hexdigest()[:16]
+    assert p == tmp_path / f"depth_{key}" and p.is_dir()
+    assert not ex.is_cached(p, 2)
+    for i in range(2):
+        (p / f"depth_{i:06d}.png").write_bytes(b"x")
+    assert ex.is_cached(p, 2) and not ex.is_cached(p, 3)
+
+
+def test_video_info_fallback_and_work_dir(tmp_path):
+    import cv2
+    from video_3d_pipeline.utils import create_work_directory, get_video_info
+    assert get_video_info(str(tmp_path / "missing.mp4")) is None
+    clip = tmp_path / "c.avi"
+    vw = cv2.VideoWriter(str(clip), cv2.VideoWriter_fourcc(*"MJPG"), 24.0, (64, 32))
+    if not vw.isOpened():
+        pytest.skip("no MJPG writer")
+    for i in range(7):
+        vw.write(np.full((32, 64, 3), i * 10, np.uint8))
+    vw.release()
+    info = get_video_info(str(clip))
+    assert info and (info["width"], info["height"], info["frames"]) == (64, 32, 7)
+    assert abs(info["fps"] - 24.0) < 1e-3 and abs(info["duration"] - 7 / 24.0) < 1e-3
+    d = create_work_directory(str(tmp_path / "wd"))
+    assert d.is_dir() and create_work_directory(str(tmp_path / "wd")) == d
+
+
+def test_frame_ranges_partition():
+    from video_3d_pipeline.shard import frame_ranges
+    for first, count, parts in ((0, 10000, 8), (10, 23, 4), (0, 3, 8), (7, 0, 2), (0, 1, 1)):
+        r = frame_ranges(first, count, parts)
+        assert len(r) == parts and sum(n for _, n in r) == count
+        assert r[0][0] == first
+        for (s0, n0), (s1, _) in zip(r, r[1:]):
+            assert s1 == s0 + n0
+        sizes = [n for _, n in r]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        frame_ranges(0, 10, 0)
+
+
+_GLOO_SCRIPT = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from video_3d_pipeline.shard import frame_ranges
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+start, n = frame_ranges(100, 37, world)[rank]
+# every rank "processes" its range; gather = host side, by global file index
+mine = torch.zeros(37, dtype=torch.int64)
+mine[start - 100:start - 100 + n] = rank + 1
+dist.all_reduce(mine)                      # only the test gathers; the product writes files instead
+ms = torch.tensor([10.0 + rank], dtype=torch.float64)
+dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # bench.py's max-over-ranks timing
+if rank == 0:
+    assert (mine > 0).all() and int((mine == 1).sum()) == 19 and int((mine == 2).sum()) == 18, mine
+    assert ms.item() == 11.0
+    print("GLOO_OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = tmp_path / "gloo_shard.py"
+    script.write_text(_GLOO_SCRIPT)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script),
+                          str(ROOT / "video-3d-pipeline_b200")], capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GLOO_OK" in out.stdout
+
+
+def test_bench_reference_arm_schema():
+    """`bench.py --impl reference` contract fields (run at a tiny size through its helpers)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    cfg = bench.workload_config(8, 2)
+    assert "workload" in cfg and cfg["global_frames_per_step"] == 16
+    assert bench.ALG_BYTES_DEPTH == 16588800 and bench.ALG_BYTES_FUSED == 53913600
+    assert bench.ALG_IOPS == 76 * 1792 * 1080 * 128

@@ -1,0 +1,229 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI (libv3d.so via ctypes),
+against the oracle -- stage by stage, bit-exact for every integer quantity."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cv2_chain
+from oracle import guided as og
+from oracle import sgbm as osg
+from video_3d_pipeline import _native as nv
+from video_3d_pipeline import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _u16(t):
+    return t.cpu().numpy().view(np.uint16)
+
+
+def _run_stages(W, H, D, mode, B=1, unsq=False, seed=7, **kw):
+    src_w = W // 2 if unsq else W
+    frames = np.stack([synthetic.sbs_frame(seed, t, src_w, H, D // 2 if unsq else D) for t in range(B)])
+    po = osg.Params(numDisparities=D, mode=mode, **kw)
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=mode, **kw), max_batch=B) as ctx:
+        ctx.set_debug_taps(True)
+        l, r = ctx.split_gray(torch.from_numpy(frames).cuda(), unsq)
+        disp = ctx.sgbm_compute(l, r)
+        C, S = _u16(ctx.debug_tap(0, B)), _u16(ctx.debug_tap(1, B))
+        raw, med = ctx.debug_tap(2, B).cpu().numpy(), ctx.debug_tap(3, B).cpu().numpy()
+        f32, u16 = ctx.postprocess(disp)
+        l, r, disp, f32, u16 = l.cpu().numpy(), r.cpu().numpy(), disp.cpu().numpy(), f32.cpu().numpy(), _u16(u16)
+    for b in range(B):
+        ol, orr = osg.split_gray(frames[b], unsq)
+        assert np.array_equal(l[b], ol) and np.array_equal(r[b], orr), "gray"
+        od, taps = osg.sgbm_compute(ol, orr, po, taps=True)
+        _, Su = osg.aggregate(taps["C"], po, unsaturated=True)
+        assert np.array_equal(C[b], taps["C"]), "cost volume"
+        assert np.array_equal(S[b], Su), "aggregated S"
+        assert np.array_equal(raw[b], taps["raw"]), "raw disparity"
+        assert np.array_equal(med[b], taps["median"]), "median"
+        assert np.array_equal(disp[b], od), "final disparity vs oracle"
+        ref = cv2_chain.make_matcher(D, mode, **kw).compute(ol, orr)
+        assert np.array_equal(disp[b], ref), "final disparity vs cv2"
+        of = osg.disp_to_float(od)
+        assert np.array_equal(f32[b], of), "float depth"
+        assert np.array_equal(u16[b], osg.normalize_u16(of)), "uint16 depth"
+
+
+@pytest.mark.parametrize("W,H,D,mode,B", [
+    (200, 120, 64, 0, 1), (200, 120, 64, 1, 1), (331, 77, 128, 0, 2), (400, 50, 256, 1, 1),
+    (67, 20, 64, 0, 1), (131, 1, 64, 0, 1), (131, 2, 64, 1, 1), (131, 3, 64, 1, 1), (259, 5, 256, 0, 1),
+    (640, 360, 128, 0, 3), (960, 270, 64, 0, 2),
+])
+def test_sgbm_stages_bit_exact(W, H, D, mode, B):
+    _run_stages(W, H, D, mode, B)
+
+
+def test_unsqueeze_path_bit_exact():
+    _run_stages(480, 270, 64, 0, B=2, unsq=True)
+
+
+@pytest.mark.parametrize("kw", [dict(speckleWindowSize=0), dict(uniquenessRatio=0), dict(uniquenessRatio=25),
+                                dict(disp12MaxDiff=3), dict(P1=100, P2=900), dict(blockSize=3), dict(blockSize=7),
+                                dict(blockSize=1), dict(preFilterCap=31), dict(speckleWindowSize=400, speckleRange=2)])
+def test_parameter_variants(kw):
+    _run_stages(230, 60, 64, 0, **kw)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "binary", "flat"])
+def test_degenerate_textures(kind):
+    rng = np.random.default_rng(3)
+    W, H, D = 150, 40, 64
+    if kind == "uniform":
+        left, right = rng.integers(0, 256, (H, W), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8)
+    elif kind == "binary":
+        left = (rng.integers(0, 2, (H, W)) * 255).astype(np.uint8)
+        right = np.roll(left, -3, axis=1)
+    else:
+        left = np.full((H, W), 77, np.uint8)
+        right = left.copy()
+    for mode in (0, 1):
+        with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=mode)) as ctx:
+            d = ctx.sgbm_compute(torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda())[0].cpu().numpy()
+        assert np.array_equal(d, cv2_chain.make_matcher(D, mode).compute(left, right))
+
+
+def test_full_size_cfg2_vs_cv2():
+    """BASELINE configs[1]: 1920x1080/eye, D=128, against the reference's cv2 call chain."""
+    W, H, D = 1920, 1080, 128
+    frame = synthetic.sbs_frame(11, 0, W, H, D)
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D)) as ctx:
+        res = ctx.depth_frames(torch.from_numpy(frame)[None].cuda(), False, want=("disp", "f32", "u16"))
+        disp, f32, u16 = res["disp"][0].cpu().numpy(), res["f32"][0].cpu().numpy(), _u16(res["u16"][0])
+    m = cv2_chain.make_matcher(D, 0)
+    l, r = cv2_chain.split_sbs_frame(frame, False)
+    ref = m.compute(cv2_chain.to_gray(l), cv2_chain.to_gray(r))
+    assert np.array_equal(disp, ref)
+    depth = cv2_chain.depth_from_sbs(frame, m, False)
+    assert np.array_equal(f32, depth)
+    assert np.array_equal(u16, cv2_chain.normalize_u16(depth))
+    assert (disp != -16).mean() > 0.5          # a real workload, not all-invalid
+
+
+def test_full_size_properties_cfg5():
+    """1920x1080, D=256, MODE_HH (BASELINE configs[4]): size-independent properties."""
+    W, H, D = 1920, 1080, 256
+    left, right, truth = synthetic.stereo_pair(13, 0, W, H, D)
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=1)) as ctx:
+        lt, rt = torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda()
+        d1 = ctx.sgbm_compute(lt, rt)[0].cpu().numpy()
+        d2 = ctx.sgbm_compute(lt, rt)[0].cpu().numpy()
+    assert np.array_equal(d1, d2)                                  # deterministic
+    assert (d1[:, :D] == -16).all()                                # columns [0, D) invalid
+    valid = d1 != -16
+    assert ((d1[valid] >= 0) & (d1[valid] <= 16 * (D - 1) + 8)).all()
+    assert valid.mean() > 0.4
+    err = np.abs(d1[valid] / 16.0 - truth[valid])
+    assert (err <= 1.0).mean() > 0.9                               # recovers the synthetic ground truth
+
+
+def test_identical_images_give_zero_disparity():
+    W, H, D = 300, 64, 64
+    left, _, _ = synthetic.stereo_pair(2, 0, W, H, D)
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D, speckleWindowSize=0)) as ctx:
+        t = torch.from_numpy(left)[None].cuda()
+        d = ctx.sgbm_compute(t, t)[0].cpu().numpy()
+    assert np.array_equal(d, cv2_chain.make_matcher(D, 0, speckleWindowSize=0).compute(left, left))
+    assert (d[:, D:] <= 8).all()
+
+
+def test_process_frame_batch_entry_bgr_eyes():
+    W, H, D = 256, 96, 64
+    frame = synthetic.sbs_frame(9, 0, W, H, D)
+    left, right = frame[:, :W], frame[:, W:]
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D)) as ctx:
+        lg = ctx.bgr_to_gray(torch.from_numpy(np.ascontiguousarray(left))[None].cuda())
+        rg = ctx.bgr_to_gray(torch.from_numpy(np.ascontiguousarray(right))[None].cuda())
+        assert np.array_equal(lg[0].cpu().numpy(), cv2_chain.to_gray(np.ascontiguousarray(left)))
+        d = ctx.sgbm_compute(lg, rg)[0].cpu().numpy()
+    assert np.array_equal(d, cv2_chain.make_matcher(D, 0).compute(cv2_chain.to_gray(np.ascontiguousarray(left)),
+                                                                  cv2_chain.to_gray(np.ascontiguousarray(right))))
+
+
+def test_unsqueeze_bgr_matches_cv2():
+    import cv2
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (2, 40, 77, 3), dtype=np.uint8)
+    out = nv.unsqueeze_bgr(torch.from_numpy(img).cuda()).cpu().numpy()
+    for b in range(2):
+        assert np.array_equal(out[b], cv2.resize(img[b], (154, 40), interpolation=cv2.INTER_LANCZOS4))
+
+
+def test_gray_odd_sizes_and_alignment():
+    rng = np.random.default_rng(4)
+    for (h, ws) in ((3, 34), (5, 70), (2, 258), (4, 1026)):
+        frame = rng.integers(0, 256, (1, h, ws, 3), dtype=np.uint8)
+        with nv.Context(max(ws // 2, 80), h, nv.SgbmParams()) as ctx:
+            l, r = ctx.split_gray(torch.from_numpy(frame).cuda(), False)
+        ol, orr = osg.split_gray(frame[0], False)
+        assert np.array_equal(l[0].cpu().numpy(), ol) and np.array_equal(r[0].cpu().numpy(), orr)
+
+
+def test_normalize_arbitrary_float_maps():
+    rng = np.random.default_rng(5)
+    maps = np.stack([rng.normal(size=(33, 47)).astype(np.float32) * 40, np.full((33, 47), 2.5, np.float32)])
+    with nv.Context(80, 8, nv.SgbmParams(), max_batch=2) as ctx:
+        out = _u16(ctx.normalize_u16(torch.from_numpy(maps).cuda()))
+    for b in range(2):
+        assert np.array_equal(out[b], cv2_chain.normalize_u16(maps[b]))
+
+
+@pytest.mark.parametrize("w,h,gw,gh,r,B", [(96, 54, 192, 108, 8, 1), (100, 60, 230, 131, 4, 1),
+                                           (480, 270, 960, 540, 8, 2), (64, 40, 64, 40, 2, 1)])
+def test_guided_upscale_within_half_lsb(w, h, gw, gh, r, B):
+    """Tolerance (north_star): 0.5 LSB of the 16-bit output on q; <= 1 LSB after rounding."""
+    d = np.stack([synthetic.depth_u16(3, t, w, h) for t in range(B)])
+    g = np.stack([synthetic.guide_frame(3, t, gw, gh) for t in range(B)])
+    with nv.Context(80, 8, nv.SgbmParams(), max_batch=B) as ctx:
+        out, q = ctx.guided_upscale(torch.from_numpy(d.view(np.int16)).cuda().view(torch.uint16),
+                                    torch.from_numpy(g).cuda(), r, 1e-3, want_q=True)
+        out, q = _u16(out), q.cpu().numpy()
+    for b in range(B):
+        oq, ou = og.guided_upscale(d[b], g[b], r, 1e-3)
+        assert np.abs(q[b] - oq).max() < 0.5 / 65535
+        assert np.abs(out[b].astype(np.int64) - ou.astype(np.int64)).max() <= 1
+
+
+def test_guided_upscale_full_4k():
+    d = synthetic.depth_u16(4, 0, 1920, 1080)
+    g = synthetic.guide_frame(4, 0, 3840, 2160)
+    with nv.Context(80, 8, nv.SgbmParams()) as ctx:
+        out, q = ctx.guided_upscale(torch.from_numpy(d.view(np.int16))[None].cuda().view(torch.uint16),
+                                    torch.from_numpy(g)[None].cuda(), 8, 1e-3, want_q=True)
+        out, q = _u16(out)[0], q[0].cpu().numpy()
+    oq, ou = og.guided_upscale(d, g, 8, 1e-3)
+    assert np.abs(q - oq).max() < 0.5 / 65535
+    assert np.abs(out.astype(np.int64) - ou.astype(np.int64)).max() <= 1
+
+
+def test_host_entry_point_matches_device_path():
+    W, H, D, B = 320, 120, 64, 3
+    frames = np.stack([synthetic.sbs_frame(6, t, W, H, D) for t in range(B)])
+    guides = np.stack([synthetic.guide_frame(6, t, 2 * W, 2 * H) for t in range(B)])
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D), max_batch=B) as ctx:
+        dev = ctx.depth_frames(torch.from_numpy(frames).cuda(), False, torch.from_numpy(guides).cuda())
+        host = dict(disp=torch.empty((B, H, W), dtype=torch.int16).pin_memory(),
+                    f32=torch.empty((B, H, W), dtype=torch.float32).pin_memory(),
+                    u16=torch.empty((B, H, W), dtype=torch.uint16).pin_memory(),
+                    out4k=torch.empty((B, 2 * H, 2 * W), dtype=torch.uint16).pin_memory())
+        n0 = ctx.launch_count
+        ctx.depth_frames_host(torch.from_numpy(frames).pin_memory(), False, torch.from_numpy(guides).pin_memory(), out=host)
+        assert ctx.launch_count > n0
+        for k in ("disp", "f32", "u16", "out4k"):
+            a, b = dev[k].cpu(), host[k]
+            assert torch.equal(a.view(torch.int16) if a.dtype == torch.uint16 else a,
+                               b.view(torch.int16) if b.dtype == torch.uint16 else b), k
+
+
+def test_bad_arguments_raise():
+    with pytest.raises(ValueError):
+        nv.Context(66, 20, nv.SgbmParams(numDisparities=64))       # cv2.error site
+    with pytest.raises(ValueError):
+        nv.Context(200, 20, nv.SgbmParams(numDisparities=48))
+    with nv.Context(200, 20, nv.SgbmParams()) as ctx:
+        with pytest.raises(ValueError):
+            ctx.split_gray(torch.zeros((1, 20, 401, 3), dtype=torch.uint8).cuda(), False)   # odd SBS width
+        with pytest.raises(ValueError):
+            ctx.sgbm_compute(torch.zeros((2, 20, 200), dtype=torch.uint8).cuda(),
+                             torch.zeros((2, 20, 200), dtype=torch.uint8).cuda())           # batch > max_batch

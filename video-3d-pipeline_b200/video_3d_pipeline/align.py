@@ -1,0 +1,63 @@
+"""Audio-based temporal alignment (reference: align.py) -- OUTSIDE the accelerated path.
+
+One cross-correlation per title is seconds of CPU work and not per-frame, so nothing here touches
+the GPU.  The class is provided so that run_pipeline.py:11,41-43 imports and runs unmodified; it
+needs the ffmpeg binary for audio extraction and raises a clear error when that is missing.
+"""
+import json
+import wave
+from pathlib import Path
+from typing import Dict
+
+import numpy as np
+
+from .utils import create_work_directory, extract_audio
+
+
+def _read_wav_mono(path: str):
+    with wave.open(path, "rb") as w:
+        rate, n, width = w.getframerate(), w.getnframes(), w.getsampwidth()
+        raw = w.readframes(n)
+    dt = {1: np.uint8, 2: np.int16, 4: np.int32}[width]
+    a = np.frombuffer(raw, dtype=dt).astype(np.float64)
+    if width == 1:
+        a -= 128.0
+    return a, rate
+
+
+class VideoAligner:
+    """find_alignment / assess_alignment_quality surface of align.py:13-116."""
+
+    def __init__(self, sbs_video_path: str, video_4k_path: str, work_dir: str = "temp_pipeline"):
+        self.sbs_video_path = sbs_video_path
+        self.video_4k_path = video_4k_path
+        self.work_dir = create_work_directory(work_dir)
+
+    def find_alignment(self, max_audio_length: float = 300) -> Dict:
+        from scipy import signal
+        a_path = extract_audio(self.sbs_video_path, str(self.work_dir / "audio_sbs.wav"), max_duration=max_audio_length)
+        b_path = extract_audio(self.video_4k_path, str(self.work_dir / "audio_4k.wav"), max_duration=max_audio_length)
+        a, rate = _read_wav_mono(a_path)
+        b, rate_b = _read_wav_mono(b_path)
+        if rate != rate_b:
+            raise ValueError("audio sample rates differ")
+        a = (a - a.mean()) / (a.std() + 1e-12)
+        b = (b - b.mean()) / (b.std() + 1e-12)
+        corr = signal.correlate(b, a, mode="full", method="fft")
+        lag = int(np.argmax(corr)) - (len(a) - 1)
+        peak = float(corr.max() / max(min(len(a), len(b)), 1))
+        data = {"time_offset_seconds": lag / float(rate), "sample_offset": lag, "sample_rate": int(rate),
+                "correlation_strength": peak, "sbs_video": self.sbs_video_path, "video_4k": self.video_4k_path}
+        with open(self.work_dir / "alignment_data.json", "w") as f:
+            json.dump(data, f, indent=2)
+        return data
+
+    def assess_alignment_quality(self, alignment_data: Dict) -> str:
+        c = float(alignment_data.get("correlation_strength", 0.0))
+        if c > 0.5:
+            return "excellent"
+        if c > 0.3:
+            return "good"
+        if c > 0.1:
+            return "fair"
+        return "poor"

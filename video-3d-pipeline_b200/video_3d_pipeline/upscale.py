@@ -1,0 +1,169 @@
+"""Guided depth upscaling on B200 -- drop-in for the reference's upscale.py.
+
+Same class / method surface as /root/reference/src/video_3d_pipeline/upscale.py.  The reference
+lets ffmpeg `scale` the 16-bit depth PNGs to the 4K size and encodes 8-bit H.264
+(upscale.py:47-59) without ever reading a 4K pixel.  Here the depth maps are upsampled with the
+4K frame itself as guide (colour guided filter, radius 8, eps 1e-3 -- the filter the reference's
+readme.md:97,119 promises) in the sm_100a kernels of libv3d.so, and written as a 16-bit PNG
+sequence (plus an 8-bit mp4 preview when an encoder is available).
+"""
+import argparse
+import glob
+import os
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import cv2
+import numpy as np
+import torch
+
+from . import _native
+from .utils import get_video_info
+
+
+class SimpleDepthUpscaler:
+    """Depth upscaling to the 4K frame size (reference class: upscale.py:12)."""
+
+    def __init__(self, use_nvenc: bool = True, radius: int = 8, eps: float = 1e-3, batch_size: int = 4,
+                 gpu_index: int = 0):
+        self.use_nvenc = use_nvenc          # kept for signature compatibility (upscale.py:15-16)
+        self.radius = int(radius)
+        self.eps = float(eps)
+        self.batch_size = int(batch_size)
+        self.gpu_index = int(gpu_index)
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA not available but requested")
+        _native.lib()
+        print("Initializing guided depth upscaler (B200 native)...")
+        self._ctx = None
+
+    def _context(self, w, h, batch):
+        c = self._ctx
+        if c is None or c.max_batch < batch:
+            if c is not None:
+                c.close()
+            # the upscale kernels only use the context for its coefficient workspace; the SGBM part
+            # is sized minimally (width must exceed numDisparities + blockSize/2)
+            self._ctx = c = _native.Context(72, 8, _native.SgbmParams(), max_batch=batch, device=self.gpu_index)
+        return c
+
+    def upscale_depth_maps_ffmpeg(self, depth_dir: str, target_width: int, target_height: int, output_path: str,
+                                  fps: float = 23.976, guide_video: str = None):
+        """upscale.py:21-73.  depth_%06d.png -> target size.  With `guide_video` (what
+        process_depth_upscaling passes) frame i of that video guides depth map i; without it the
+        upsampled depth guides itself."""
+        print("Processing depth upscaling on GPU...")
+        print(f"Input: {depth_dir}")
+        print(f"Output: {output_path}")
+        print(f"Target: {target_width}x{target_height} @ {fps}fps")
+        depth_files = sorted(glob.glob(os.path.join(depth_dir, "depth_*.png")))
+        if not depth_files:
+            raise ValueError(f"No depth maps found in {depth_dir}")           # upscale.py:37-38
+        print(f"Found {len(depth_files)} depth maps")
+
+        out_path = Path(output_path)
+        png_dir = out_path.with_suffix("")
+        png_dir = png_dir.parent / (png_dir.name + "_png16")
+        png_dir.mkdir(parents=True, exist_ok=True)
+        writer = cv2.VideoWriter(str(out_path), cv2.VideoWriter_fourcc(*"mp4v"), float(fps),
+                                 (int(target_width), int(target_height)), False)
+        if not writer.isOpened():
+            writer = None
+
+        cap = None
+        if guide_video is not None:
+            cap = cv2.VideoCapture(str(guide_video))
+            if not cap.isOpened():
+                raise ValueError(f"Could not open video file: {guide_video}")
+        dev = torch.device("cuda", self.gpu_index)
+        pool = ThreadPoolExecutor(max_workers=4)
+        pending = []
+        try:
+            for s in range(0, len(depth_files), self.batch_size):
+                files = depth_files[s:s + self.batch_size]
+                maps = []
+                for f in files:
+                    d = cv2.imread(f, cv2.IMREAD_UNCHANGED)
+                    if d is None or d.ndim != 2:
+                        raise ValueError(f"Unreadable depth map: {f}")
+                    maps.append(d.astype(np.uint16) if d.dtype == np.uint16 else (d.astype(np.uint16) * 257))
+                guides = []
+                for d in maps:
+                    frame = None
+                    if cap is not None:
+                        ok, frame = cap.read()
+                        frame = frame if ok else None
+                    if frame is None:       # self-guided
+                        g8 = (cv2.resize(d, (target_width, target_height), interpolation=cv2.INTER_LINEAR) >> 8).astype(np.uint8)
+                        frame = np.repeat(g8[..., None], 3, axis=2)
+                    elif frame.shape[1] != target_width or frame.shape[0] != target_height:
+                        frame = cv2.resize(frame, (target_width, target_height), interpolation=cv2.INTER_AREA)
+                    guides.append(frame[..., ::-1])                         # BGR -> RGB guide
+                ctx = self._context(target_width, target_height, len(maps))
+                d_t = torch.from_numpy(np.stack(maps).view(np.int16)).to(dev).view(torch.uint16)
+                g_t = torch.from_numpy(np.ascontiguousarray(np.stack(guides))).to(dev)
+                out = ctx.guided_upscale(d_t, g_t, self.radius, self.eps).cpu().numpy().view(np.uint16)
+                for i in range(len(maps)):
+                    pending.append(pool.submit(cv2.imwrite, str(png_dir / f"depth4k_{s + i:06d}.png"), out[i].copy()))
+                    if writer is not None:
+                        writer.write((out[i] >> 8).astype(np.uint8))
+            for f in pending:
+                f.result()
+        finally:
+            pool.shutdown(wait=True)
+            if cap is not None:
+                cap.release()
+            if writer is not None:
+                writer.release()
+        if not out_path.exists():          # no encoder in this OpenCV build: leave a pointer file
+            out_path.write_text(f"16-bit PNG sequence: {png_dir}\n")
+        print(f"✓ Depth video saved: {output_path}  (16-bit frames: {png_dir})")
+        return output_path
+
+    def process_depth_upscaling(self, depth_dir: str, video_4k_path: str, output_path: str = None,
+                                force_reprocess: bool = False) -> str:
+        """upscale.py:75-123."""
+        print("Processing depth upscaling...")
+        print(f"Depth maps: {depth_dir}")
+        print(f"4K video: {video_4k_path}")
+        info = get_video_info(video_4k_path)
+        if not info:
+            raise ValueError(f"Could not read video info: {video_4k_path}")   # upscale.py:88-89
+        tw, th, fps = info["width"], info["height"], info["fps"]
+        print(f"Target resolution: {tw}x{th} @ {fps}fps")
+        if output_path is None:
+            output_path = f"depth_4k_{Path(depth_dir).name}.mp4"               # upscale.py:98-100
+        output_path = Path(output_path)
+        if output_path.exists() and not force_reprocess:                      # upscale.py:104-107
+            print(f"✓ Using existing depth video: {output_path}")
+            return str(output_path)
+        result = self.upscale_depth_maps_ffmpeg(depth_dir=str(depth_dir), target_width=tw, target_height=th,
+                                                output_path=str(output_path), fps=fps or 23.976,
+                                                guide_video=video_4k_path)
+        print("✓ Depth upscaling complete!")
+        print(f"  Resolution: {tw}x{th}")
+        return result
+
+
+def main():
+    """Command line interface (upscale.py:126-158)."""
+    parser = argparse.ArgumentParser(description="Guided depth upscaling on GPU")
+    parser.add_argument("depth_dir", help="Directory containing depth maps")
+    parser.add_argument("video_4k", help="Path to 4K 2D video (dimensions and guide frames)")
+    parser.add_argument("--output", help="Output path for 4K depth video")
+    parser.add_argument("--no-nvenc", action="store_true")
+    parser.add_argument("--force", action="store_true")
+    args = parser.parse_args()
+    try:
+        upscaler = SimpleDepthUpscaler(use_nvenc=not args.no_nvenc)
+        out = upscaler.process_depth_upscaling(depth_dir=args.depth_dir, video_4k_path=args.video_4k,
+                                               output_path=args.output, force_reprocess=args.force)
+        print(f"\n✓ Success! 4K depth video: {out}")
+    except Exception as e:
+        print(f"Error: {e}")
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
