@@ -14,6 +14,7 @@
 namespace {
 
 constexpr int GT = 32;      // tile edge
+constexpr int GRUN = 8;     // outputs per thread along the filtered axis (first direct, the rest slid)
 constexpr int GRMAX = 8;    // largest supported radius
 
 __device__ __forceinline__ int reflect_idx(int i, int n)
@@ -24,24 +25,15 @@ __device__ __forceinline__ int reflect_idx(int i, int n)
     return min(max(i, 0), n - 1);
 }
 
-// Bilinear sample of depth/65535 at guide pixel (X, Y): half-pixel centres, clamped taps.  The source
-// coordinate is formed in integers ((2X+1)*w - gw over 2*gw) so that only the final weights are rounded.
-__device__ __forceinline__ float sample_depth(const uint16_t* __restrict__ d, int w, int h, int gw, int gh, int X, int Y)
+// Bilinear tap of one axis at guide coordinate X (already reflected): half-pixel centres, clamped taps.
+// The source coordinate is formed in integers ((2X+1)*w - gw over 2*gw) so that only the weight is rounded.
+__device__ __forceinline__ void axis_tap(int X, int w, int gw, int& i0, int& i1, float& f)
 {
-    const int nx = (2 * X + 1) * w - gw, ny = (2 * Y + 1) * h - gh;
-    const int dx2 = 2 * gw, dy2 = 2 * gh;
-    int x0 = nx >= 0 ? nx / dx2 : -((-nx + dx2 - 1) / dx2);
-    int y0 = ny >= 0 ? ny / dy2 : -((-ny + dy2 - 1) / dy2);
-    const float fx = __fdiv_rn((float)(nx - x0 * dx2), (float)dx2);
-    const float fy = __fdiv_rn((float)(ny - y0 * dy2), (float)dy2);
-    const int x1 = min(max(x0 + 1, 0), w - 1), y1 = min(max(y0 + 1, 0), h - 1);
-    x0 = min(max(x0, 0), w - 1); y0 = min(max(y0, 0), h - 1);
-    const float s = 1.0f / 65535.0f;
-    const float p00 = __ldg(d + (size_t)y0 * w + x0) * s, p01 = __ldg(d + (size_t)y0 * w + x1) * s;
-    const float p10 = __ldg(d + (size_t)y1 * w + x0) * s, p11 = __ldg(d + (size_t)y1 * w + x1) * s;
-    const float top = p00 * (1.0f - fx) + p01 * fx;
-    const float bot = p10 * (1.0f - fx) + p11 * fx;
-    return top * (1.0f - fy) + bot * fy;
+    const int n = (2 * X + 1) * w - gw, d2 = 2 * gw;
+    int q = n >= 0 ? n / d2 : -((-n + d2 - 1) / d2);
+    f = __fdiv_rn((float)(n - q * d2), (float)d2);
+    i1 = min(max(q + 1, 0), w - 1);
+    i0 = min(max(q, 0), w - 1);
 }
 
 __device__ __forceinline__ float3 load_guide(const uint8_t* __restrict__ g, int gw, int X, int Y)
@@ -51,91 +43,131 @@ __device__ __forceinline__ float3 load_guide(const uint8_t* __restrict__ g, int 
     return make_float3(__ldg(p) * s, __ldg(p + 1) * s, __ldg(p + 2) * s);
 }
 
+__device__ __forceinline__ void moments13(const float4& v, float (&m)[13])
+{
+    m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+    m[4] = v.x * v.w; m[5] = v.y * v.w; m[6] = v.z * v.w;
+    m[7] = v.x * v.x; m[8] = v.x * v.y; m[9] = v.x * v.z;
+    m[10] = v.y * v.y; m[11] = v.y * v.z; m[12] = v.z * v.z;
+}
+
+struct TileTaps {           // per-tile sampling tables (one entry per region column / row)
+    int gx[GT + 2 * GRMAX], gy[GT + 2 * GRMAX];              // reflected guide coordinates
+    int x0[GT + 2 * GRMAX], x1[GT + 2 * GRMAX], y0[GT + 2 * GRMAX], y1[GT + 2 * GRMAX];
+    float fx[GT + 2 * GRMAX], fy[GT + 2 * GRMAX];
+};
+
 // ------------------------------------------------------------------------------------------------
+// RT > 0: radius known at compile time (the loops unroll); RT == 0: runtime radius.
+template <int RT>
 __global__ void __launch_bounds__(256)
 k_guided_coeff(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* __restrict__ guide, int gw, int gh,
-               int r, float eps, float4* __restrict__ ab)
+               int r_arg, float eps, float4* __restrict__ ab)
 {
     extern __shared__ float4 gsm[];
+    const int r = RT > 0 ? RT : r_arg;
     const int RW = GT + 2 * r, RH = GT + 2 * r, BP = RW + 1;          // base pitch (float4), odd -> conflict free
-    float4* base = gsm;                                                 // [RH][BP]
-    float* hs = reinterpret_cast<float*>(gsm + (size_t)RH * BP);       // [13][RH][33]
     const int HP = GT + 1;
+    float4* base = gsm;                                                 // [RH][BP]
+    float* hs = reinterpret_cast<float*>(gsm + (size_t)RH * BP);       // [13][RH][HP]
+    __shared__ TileTaps tp;
+    __shared__ float4 centre;
     const int tid = threadIdx.x;
     const int X0 = blockIdx.x * GT, Y0 = blockIdx.y * GT, b = blockIdx.z;
     depth += (size_t)b * w * h;
     guide += (size_t)b * gw * gh * 3;
     ab += (size_t)b * gw * gh;
 
-    // per-tile centre
-    const int Xc = min(X0 + GT / 2, gw - 1), Yc = min(Y0 + GT / 2, gh - 1);
-    const float3 cI = load_guide(guide, gw, Xc, Yc);
-    const float cp = sample_depth(depth, w, h, gw, gh, Xc, Yc);
-
-    for (int i = tid; i < RW * RH; i += blockDim.x) {
+    if (tid < RW) {
+        const int X = reflect_idx(X0 - r + tid, gw);
+        tp.gx[tid] = X;
+        axis_tap(X, w, gw, tp.x0[tid], tp.x1[tid], tp.fx[tid]);
+    } else if (tid >= 64 && tid < 64 + RH) {
+        const int j = tid - 64;
+        const int Y = reflect_idx(Y0 - r + j, gh);
+        tp.gy[j] = Y;
+        axis_tap(Y, h, gh, tp.y0[j], tp.y1[j], tp.fy[j]);
+    }
+    __syncthreads();
+    auto sample = [&](int t, int j) -> float4 {
+        const float3 I = load_guide(guide, gw, tp.gx[t], tp.gy[j]);
+        const float s = 1.0f / 65535.0f;
+        const uint16_t* r0 = depth + (size_t)tp.y0[j] * w;
+        const uint16_t* r1 = depth + (size_t)tp.y1[j] * w;
+        const float fx = tp.fx[t], fy = tp.fy[j];
+        const float p00 = __ldg(r0 + tp.x0[t]) * s, p01 = __ldg(r0 + tp.x1[t]) * s;
+        const float p10 = __ldg(r1 + tp.x0[t]) * s, p11 = __ldg(r1 + tp.x1[t]) * s;
+        const float top = p00 * (1.0f - fx) + p01 * fx;
+        const float bot = p10 * (1.0f - fx) + p11 * fx;
+        return make_float4(I.x, I.y, I.z, top * (1.0f - fy) + bot * fy);
+    };
+    // per-tile centre: moments are taken about it (box sums are shift covariant)
+    if (tid == 0) centre = sample(min(r + GT / 2, RW - 1), min(r + GT / 2, RH - 1));
+    __syncthreads();
+    const float4 cc = centre;
+    for (int i = tid; i < RW * RH; i += 256) {
         const int j = i / RW, t = i - j * RW;
-        const int X = reflect_idx(X0 - r + t, gw), Y = reflect_idx(Y0 - r + j, gh);
-        const float3 I = load_guide(guide, gw, X, Y);
-        const float p = sample_depth(depth, w, h, gw, gh, X, Y);
-        base[j * BP + t] = make_float4(I.x - cI.x, I.y - cI.y, I.z - cI.z, p - cp);
+        const float4 v = sample(t, j);
+        base[j * BP + t] = make_float4(v.x - cc.x, v.y - cc.y, v.z - cc.z, v.w - cc.w);
     }
     __syncthreads();
 
-    // horizontal sums: item = (row j, group of 4 output columns)
-    for (int it = tid; it < RH * (GT / 4); it += blockDim.x) {
+    // horizontal box sums: item = (row j, run of GRUN output columns); first output direct, rest slid
+    for (int it = tid; it < RH * (GT / GRUN); it += 256) {
         const int j = it % RH, g = it / RH;
-        float acc[4][13];
+        const float4* row = base + j * BP + g * GRUN;
+        float acc[13], m[13];
 #pragma unroll
-        for (int o = 0; o < 4; o++)
+        for (int q = 0; q < 13; q++) acc[q] = 0.0f;
+#pragma unroll 1
+        for (int t = 0; t <= 2 * r; t++) {
+            moments13(row[t], m);
 #pragma unroll
-            for (int m = 0; m < 13; m++) acc[o][m] = 0.0f;
-        const float4* row = base + j * BP + g * 4;
-        for (int t = 0; t < 4 + 2 * r; t++) {
-            const float4 v = row[t];
-            const float m[13] = { v.x, v.y, v.z, v.w, v.x * v.w, v.y * v.w, v.z * v.w,
-                                  v.x * v.x, v.x * v.y, v.x * v.z, v.y * v.y, v.y * v.z, v.z * v.z };
-#pragma unroll
-            for (int o = 0; o < 4; o++)
-                if (t >= o && t <= o + 2 * r) {
-#pragma unroll
-                    for (int q = 0; q < 13; q++) acc[o][q] += m[q];
-                }
+            for (int q = 0; q < 13; q++) acc[q] += m[q];
         }
+        float* out = hs + (size_t)j * HP + g * GRUN;
 #pragma unroll
-        for (int m = 0; m < 13; m++)
+        for (int q = 0; q < 13; q++) out[(size_t)q * RH * HP] = acc[q];
+#pragma unroll 1
+        for (int o = 1; o < GRUN; o++) {
+            moments13(row[o + 2 * r], m);
 #pragma unroll
-            for (int o = 0; o < 4; o++) hs[((size_t)m * RH + j) * HP + g * 4 + o] = acc[o][m];
+            for (int q = 0; q < 13; q++) acc[q] += m[q];
+            moments13(row[o - 1], m);
+#pragma unroll
+            for (int q = 0; q < 13; q++) acc[q] -= m[q];
+#pragma unroll
+            for (int q = 0; q < 13; q++) out[(size_t)q * RH * HP + o] = acc[q];
+        }
     }
     __syncthreads();
 
-    // vertical sums + solve: thread = (column, group of 4 output rows)
-    {
+    // vertical box sums + 3x3 solve: item = (column, run of GRUN output rows)
+    if (tid < GT * (GT / GRUN)) {
         const int col = tid & 31, rg = tid >> 5;
-        float acc[4][13];
+        const float* hc = hs + (size_t)(rg * GRUN) * HP + col;
+        float acc[13];
 #pragma unroll
-        for (int o = 0; o < 4; o++)
+        for (int q = 0; q < 13; q++) acc[q] = 0.0f;
+#pragma unroll 1
+        for (int t = 0; t <= 2 * r; t++) {
 #pragma unroll
-            for (int m = 0; m < 13; m++) acc[o][m] = 0.0f;
-        for (int t = 0; t < 4 + 2 * r; t++) {
-            float m[13];
-#pragma unroll
-            for (int q = 0; q < 13; q++) m[q] = hs[((size_t)q * RH + rg * 4 + t) * HP + col];
-#pragma unroll
-            for (int o = 0; o < 4; o++)
-                if (t >= o && t <= o + 2 * r) {
-#pragma unroll
-                    for (int q = 0; q < 13; q++) acc[o][q] += m[q];
-                }
+            for (int q = 0; q < 13; q++) acc[q] += hc[((size_t)q * RH + t) * HP];
         }
         const float inv_n = 1.0f / (float)((2 * r + 1) * (2 * r + 1));
         const int X = X0 + col;
+#pragma unroll 1
+        for (int o = 0; o < GRUN; o++) {
+            if (o > 0) {
 #pragma unroll
-        for (int o = 0; o < 4; o++) {
-            const int Y = Y0 + rg * 4 + o;
+                for (int q = 0; q < 13; q++)
+                    acc[q] += hc[((size_t)q * RH + o + 2 * r) * HP] - hc[((size_t)q * RH + o - 1) * HP];
+            }
+            const int Y = Y0 + rg * GRUN + o;
             if (X >= gw || Y >= gh) continue;
             float m[13];
 #pragma unroll
-            for (int q = 0; q < 13; q++) m[q] = acc[o][q] * inv_n;
+            for (int q = 0; q < 13; q++) m[q] = acc[q] * inv_n;
             const float mI0 = m[0], mI1 = m[1], mI2 = m[2], mp = m[3];
             const float c0 = m[4] - mI0 * mp, c1 = m[5] - mI1 * mp, c2 = m[6] - mI2 * mp;
             const float s00 = m[7] - mI0 * mI0 + eps, s01 = m[8] - mI0 * mI1, s02 = m[9] - mI0 * mI2;
@@ -148,18 +180,23 @@ k_guided_coeff(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* 
             const float a1 = (k01 * c0 + k11 * c1 + k12 * c2) * idet;
             const float a2 = (k02 * c0 + k12 * c1 + k22 * c2) * idet;
             // b referred to a guide centred at 0.5:  q = a.(I - 0.5) + b
-            const float bb = (mp + cp) - a0 * (mI0 + cI.x - 0.5f) - a1 * (mI1 + cI.y - 0.5f) - a2 * (mI2 + cI.z - 0.5f);
+            const float bb = (mp + cc.w) - a0 * (mI0 + cc.x - 0.5f) - a1 * (mI1 + cc.y - 0.5f) - a2 * (mI2 + cc.z - 0.5f);
             ab[(size_t)Y * gw + X] = make_float4(a0, a1, a2, bb);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void sub4(float4& a, const float4& b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; a.w -= b.w; }
+
+template <int RT>
 __global__ void __launch_bounds__(256)
-k_guided_apply(const float4* __restrict__ ab, const uint8_t* __restrict__ guide, int gw, int gh, int r,
+k_guided_apply(const float4* __restrict__ ab, const uint8_t* __restrict__ guide, int gw, int gh, int r_arg,
                uint16_t* __restrict__ out, float* __restrict__ qout)
 {
     extern __shared__ float4 gsm[];
+    const int r = RT > 0 ? RT : r_arg;
     const int RW = GT + 2 * r, RH = GT + 2 * r, BP = RW + 1, HP = GT + 1;
     float4* base = gsm;                               // [RH][BP]
     float4* hs = gsm + (size_t)RH * BP;               // [RH][HP]
@@ -170,52 +207,72 @@ k_guided_apply(const float4* __restrict__ ab, const uint8_t* __restrict__ guide,
     out += (size_t)b * gw * gh;
     if (qout) qout += (size_t)b * gw * gh;
 
-    for (int i = tid; i < RW * RH; i += blockDim.x) {
+    for (int i = tid; i < RW * RH; i += 256) {
         const int j = i / RW, t = i - j * RW;
         const int X = reflect_idx(X0 - r + t, gw), Y = reflect_idx(Y0 - r + j, gh);
         base[j * BP + t] = __ldg(ab + (size_t)Y * gw + X);
     }
     __syncthreads();
-    for (int it = tid; it < RH * (GT / 4); it += blockDim.x) {
+    for (int it = tid; it < RH * (GT / GRUN); it += 256) {
         const int j = it % RH, g = it / RH;
-        float4 acc[4];
+        const float4* row = base + j * BP + g * GRUN;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int t = 0; t <= 2 * r; t++) add4(acc, row[t]);
+        float4* o4 = hs + j * HP + g * GRUN;
+        o4[0] = acc;
 #pragma unroll
-        for (int o = 0; o < 4; o++) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* row = base + j * BP + g * 4;
-        for (int t = 0; t < 4 + 2 * r; t++) {
-            const float4 v = row[t];
-#pragma unroll
-            for (int o = 0; o < 4; o++)
-                if (t >= o && t <= o + 2 * r) { acc[o].x += v.x; acc[o].y += v.y; acc[o].z += v.z; acc[o].w += v.w; }
-        }
-#pragma unroll
-        for (int o = 0; o < 4; o++) hs[j * HP + g * 4 + o] = acc[o];
+        for (int o = 1; o < GRUN; o++) { add4(acc, row[o + 2 * r]); sub4(acc, row[o - 1]); o4[o] = acc; }
     }
     __syncthreads();
-    {
+    if (tid < GT * (GT / GRUN)) {
         const int col = tid & 31, rg = tid >> 5;
-        float4 acc[4];
-#pragma unroll
-        for (int o = 0; o < 4; o++) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = 0; t < 4 + 2 * r; t++) {
-            const float4 v = hs[(rg * 4 + t) * HP + col];
-#pragma unroll
-            for (int o = 0; o < 4; o++)
-                if (t >= o && t <= o + 2 * r) { acc[o].x += v.x; acc[o].y += v.y; acc[o].z += v.z; acc[o].w += v.w; }
-        }
+        const float4* hc = hs + (rg * GRUN) * HP + col;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int t = 0; t <= 2 * r; t++) add4(acc, hc[t * HP]);
         const float inv_n = 1.0f / (float)((2 * r + 1) * (2 * r + 1));
         const int X = X0 + col;
 #pragma unroll
-        for (int o = 0; o < 4; o++) {
-            const int Y = Y0 + rg * 4 + o;
+        for (int o = 0; o < GRUN; o++) {
+            if (o > 0) { add4(acc, hc[(o + 2 * r) * HP]); sub4(acc, hc[(o - 1) * HP]); }
+            const int Y = Y0 + rg * GRUN + o;
             if (X >= gw || Y >= gh) continue;
             const float3 I = load_guide(guide, gw, X, Y);
-            const float q = (acc[o].x * (I.x - 0.5f) + acc[o].y * (I.y - 0.5f) + acc[o].z * (I.z - 0.5f) + acc[o].w) * inv_n;
+            const float q = (acc.x * (I.x - 0.5f) + acc.y * (I.y - 0.5f) + acc.z * (I.z - 0.5f) + acc.w) * inv_n;
             const float qc = fminf(fmaxf(q, 0.0f), 1.0f);
             out[(size_t)Y * gw + X] = (uint16_t)floorf(qc * 65535.0f + 0.5f);
             if (qout) qout[(size_t)Y * gw + X] = q;
         }
     }
+}
+
+constexpr size_t sm_coeff_max()
+{
+    return (size_t)(GT + 2 * GRMAX) * (GT + 2 * GRMAX + 1) * 16 + (size_t)13 * (GT + 2 * GRMAX) * (GT + 1) * 4;
+}
+constexpr size_t sm_apply_max()
+{
+    return (size_t)(GT + 2 * GRMAX) * (GT + 2 * GRMAX + 1) * 16 + (size_t)(GT + 2 * GRMAX) * (GT + 1) * 16;
+}
+
+template <int RT>
+int launch_guided_rt(v3d_ctx* ctx, const uint16_t* depth, int w, int h, const uint8_t* guide, int gw, int gh,
+                     int batch, int r, float eps, uint16_t* out, float* q, cudaStream_t st)
+{
+    const int RW = GT + 2 * r;
+    const size_t sm_coeff = (size_t)RW * (RW + 1) * sizeof(float4) + (size_t)13 * RW * (GT + 1) * sizeof(float);
+    const size_t sm_apply = (size_t)RW * (RW + 1) * sizeof(float4) + (size_t)RW * (GT + 1) * sizeof(float4);
+    if (!(ctx->guided_attr_set & (1 << RT))) {
+        V3D_CUDA(cudaFuncSetAttribute(k_guided_coeff<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_coeff_max()));
+        V3D_CUDA(cudaFuncSetAttribute(k_guided_apply<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_apply_max()));
+        ctx->guided_attr_set |= (1 << RT);
+    }
+    dim3 grid((gw + GT - 1) / GT, (gh + GT - 1) / GT, batch);
+    k_guided_coeff<RT><<<grid, 256, sm_coeff, st>>>(depth, w, h, guide, gw, gh, r, eps, ctx->ab);
+    k_guided_apply<RT><<<grid, 256, sm_apply, st>>>(ctx->ab, guide, gw, gh, r, out, q);
+    V3D_LAUNCHED(ctx, 2);
+    return V3D_OK;
 }
 
 }  // namespace
@@ -232,20 +289,9 @@ int v3d_launch_guided(v3d_ctx* ctx, const uint16_t* depth, int w, int h, const u
         ctx->ab_bytes = need; ctx->bytes += need;
     }
     V3dScope scope(ctx, ST_GUIDED, st);
-    const int RW = GT + 2 * r;
-    const size_t sm_coeff = (size_t)RW * (RW + 1) * sizeof(float4) + (size_t)13 * RW * (GT + 1) * sizeof(float);
-    const size_t sm_apply = (size_t)RW * (RW + 1) * sizeof(float4) + (size_t)RW * (GT + 1) * sizeof(float4);
-    if (!ctx->guided_attr_set) {
-        const int RWm = GT + 2 * GRMAX;
-        V3D_CUDA(cudaFuncSetAttribute(k_guided_coeff, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((size_t)RWm * (RWm + 1) * 16 + (size_t)13 * RWm * (GT + 1) * 4)));
-        V3D_CUDA(cudaFuncSetAttribute(k_guided_apply, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((size_t)RWm * (RWm + 1) * 16 + (size_t)RWm * (GT + 1) * 16)));
-        ctx->guided_attr_set = 1;
+    switch (r) {
+        case 8: return launch_guided_rt<8>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);
+        case 4: return launch_guided_rt<4>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);
+        default: return launch_guided_rt<0>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);
     }
-    dim3 grid((gw + GT - 1) / GT, (gh + GT - 1) / GT, batch);
-    k_guided_coeff<<<grid, 256, sm_coeff, st>>>(depth, w, h, guide, gw, gh, r, eps, ctx->ab);
-    k_guided_apply<<<grid, 256, sm_apply, st>>>(ctx->ab, guide, gw, gh, r, out, q);
-    V3D_LAUNCHED(ctx, 2);
-    return V3D_OK;
 }

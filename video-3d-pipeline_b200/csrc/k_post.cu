@@ -127,32 +127,70 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b)
     } while (!done);
 }
 
-__global__ void __launch_bounds__(256)
-k_ccl_init(int* __restrict__ L, int* __restrict__ sizes, int n_total)
+__device__ __forceinline__ bool ccl_edge(int a, int b, int maxDiff)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_total) { L[i] = i; sizes[i] = 0; }
+    return a != INV && b != INV && abs(a - b) <= maxDiff;
 }
 
+// Pass 1, one block per image row: every valid pixel is labelled with the index of the first pixel
+// of its horizontal run (inclusive max-scan of "run starts here" positions), so that union-find
+// chains start one hop deep instead of a row long.
 // labels are indices into the whole batch buffer (frame b occupies [b*n, (b+1)*n))
+__global__ void __launch_bounds__(256)
+k_ccl_rows(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
+           int* __restrict__ sizes, int W, int H, int maxDiff)
+{
+    __shared__ int wmax[8];
+    __shared__ int carry_s;
+    const int y = blockIdx.x % H, b = blockIdx.x / H;
+    const int16_t* d = disp + (size_t)b * dstride_e + (size_t)y * dpitch_e;
+    const int rowbase = (b * H + y) * W;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = -1;
+    __syncthreads();
+    for (int x0 = 0; x0 < W; x0 += 256) {
+        const int x = x0 + threadIdx.x;
+        int start = -1;
+        if (x < W) {
+            const int v = d[x];
+            const bool left = x > 0 && ccl_edge(v, d[x - 1], maxDiff);
+            if (!left) start = x;                     // a run (or an invalid pixel) starts here
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(V3D_FULL_MASK, start, o);
+            if (lane >= o) start = max(start, t);
+        }
+        if (lane == 31) wmax[wid] = start;
+        __syncthreads();
+        int pre = carry_s;
+        for (int w = 0; w < wid; w++) pre = max(pre, wmax[w]);
+        start = max(start, pre);
+        if (x < W) { L[rowbase + x] = rowbase + start; sizes[rowbase + x] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = start;
+        __syncthreads();
+    }
+}
+
+// Pass 2: vertical unions.  A union is skipped when the pixel's left neighbour already carries it
+// (x-1,y)~(x,y), (x-1,y-1)~(x,y-1) and (x-1,y)~(x-1,y-1) all hold.
 __global__ void __launch_bounds__(256)
 k_ccl_merge(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
             int W, int H, int maxDiff)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
+    if (x >= W || y == 0) return;
     const int16_t* d = disp + (size_t)b * dstride_e;
     const int v = d[(size_t)y * dpitch_e + x];
-    if (v == INV) return;
-    const int i = (b * H + y) * W + x;
+    const int u = d[(size_t)(y - 1) * dpitch_e + x];
+    if (!ccl_edge(v, u, maxDiff)) return;
     if (x > 0) {
-        const int u = d[(size_t)y * dpitch_e + x - 1];
-        if (u != INV && abs(u - v) <= maxDiff) uf_union(L, i, i - 1);
+        const int vl = d[(size_t)y * dpitch_e + x - 1], ul = d[(size_t)(y - 1) * dpitch_e + x - 1];
+        if (ccl_edge(v, vl, maxDiff) && ccl_edge(u, ul, maxDiff) && ccl_edge(vl, ul, maxDiff)) return;
     }
-    if (y > 0) {
-        const int u = d[(size_t)(y - 1) * dpitch_e + x];
-        if (u != INV && abs(u - v) <= maxDiff) uf_union(L, i, i - W);
-    }
+    const int i = (b * H + y) * W + x;
+    uf_union(L, i, i - W);
 }
 
 __global__ void __launch_bounds__(256)
@@ -314,7 +352,7 @@ int v3d_launch_speckle(v3d_ctx* ctx, int batch, int16_t* disp, size_t dpitch, si
     const int n_total = batch * W * H;
     const int maxDiff = 16 * ctx->p.speckleRange;
     dim3 grid((W + 255) / 256, H, batch);
-    k_ccl_init<<<(n_total + 255) / 256, 256, 0, st>>>(ctx->labels, ctx->sizes, n_total);
+    k_ccl_rows<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H, maxDiff);
     k_ccl_merge<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff);
     k_ccl_count<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H);
     k_ccl_apply<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H,
