@@ -321,6 +321,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "stages_ms_per_step": stages,
             "workspace_gb": ctx.workspace_bytes / 1e9,
+            "fused_sweep_clusters": ctx.fused_sweep_clusters,
         }
     ctx.close()
     if world > 1:

@@ -159,6 +159,10 @@ int v3d_depth_frames_host(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, 
                           uint16_t* depth_u16_host, const uint8_t* guide_rgb_host, int gw, int gh,
                           int r, float eps, uint16_t* out_4k_host, void* stream);
 
+/* How many frames the fused vertical sweep keeps co-resident on this device (one thread-block
+ * cluster per frame); batches that are a multiple of it leave no partial wave.  0 until the first
+ * v3d_sgbm_compute call, or when the shape uses the unfused path kernels. */
+int v3d_fused_sweep_clusters(const v3d_ctx* ctx);
 /* Number of kernel launches issued through this context so far. */
 unsigned long long v3d_launch_count(const v3d_ctx* ctx);
 /* Record per-stage CUDA-event timings for subsequent calls (0 = off).  With

@@ -13,6 +13,9 @@
 // A predecessor outside the window contributes L = 0, i.e. M = 0, which is also the initial state.
 #include "v3d_internal.h"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace {
 
 template <int NR> struct Vec;
@@ -265,6 +268,174 @@ k_path_rl_wta(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, uint2*
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// The three directions of one vertical sweep fused: (x, y-sy), (x-1, y-sy), (x+1, y-sy).
+// One thread-block CLUSTER of V3_CL CTAs owns a whole frame; warp g of the cluster owns the CPW
+// consecutive columns [g*CPW, (g+1)*CPW) for every row and every direction, so C is read once and
+// S is written once per sweep instead of three reads of C and a write + two read-modify-writes of S.
+// Path state M lives in shared memory ([dir][column][d]); a diagonal path moves to the neighbouring
+// column every row, so the only inter-warp traffic is one 2*NR*64-byte state vector per warp
+// boundary and direction per row, exchanged through (distributed) shared memory behind one cluster
+// barrier per row.
+// ------------------------------------------------------------------------------------------
+constexpr int V3_CL = 8;     // CTAs per cluster (portable maximum)
+constexpr int V3_NW = 32;    // warps per CTA
+
+template <int NR, int CPW, int SMODE>
+__global__ void __launch_bounds__(V3_NW * 32, 1)
+k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, int H, int sy,
+             uint32_t P1p, uint32_t P2p)
+{
+    using VT = typename Vec<NR>::T;
+    extern __shared__ uint4 v3smem[];
+    constexpr int COLS = V3_NW * CPW;
+    VT* Mst = reinterpret_cast<VT*>(v3smem);          // [3][COLS][32]   path state
+    VT* xch = Mst + 3 * COLS * 32;                    // [2][V3_NW][2][32] boundary exchange, double buffered
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int frame = blockIdx.x / V3_CL;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gcol0 = (rank * V3_NW + w) * CPW;       // first column this warp owns
+    const int lc0 = w * CPW;
+    const VT* C = reinterpret_cast<const VT*>(Cv) + (size_t)frame * H * W1 * 32 + lane;
+    VT* S = reinterpret_cast<VT*>(Sv) + (size_t)frame * H * W1 * 32 + lane;
+
+    uint32_t zr[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) zr[r] = 0;
+    const VT zero = pack<NR>(zr);
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int j = 0; j < CPW; j++) Mst[((d * COLS) + lc0 + j) * 32 + lane] = zero;
+
+    // where the neighbours publish: slot 0 = last column's (x-1)-direction state, slot 1 = first column's (x+1) one
+    const VT* left_x = nullptr;
+    const VT* right_x = nullptr;
+    if (w > 0) left_x = xch + ((w - 1) * 2 + 0) * 32 + lane;
+    else if (rank > 0) left_x = cluster.map_shared_rank(xch, rank - 1) + ((V3_NW - 1) * 2 + 0) * 32 + lane;
+    if (w < V3_NW - 1) right_x = xch + ((w + 1) * 2 + 1) * 32 + lane;
+    else if (rank < V3_CL - 1) right_x = cluster.map_shared_rank(xch, rank + 1) + (0 * 2 + 1) * 32 + lane;
+    constexpr int PARSTRIDE = V3_NW * 2 * 32;
+
+    VT cq[CPW], sq[CPW];
+    {
+        const int y = sy > 0 ? 0 : H - 1;
+#pragma unroll
+        for (int j = 0; j < CPW; j++)
+            if (gcol0 + j < W1) {
+                cq[j] = __ldg(C + ((size_t)y * W1 + gcol0 + j) * 32);
+                if (SMODE == S_ACCUM) sq[j] = S[((size_t)y * W1 + gcol0 + j) * 32];
+            }
+    }
+    for (int i = 0; i < H; i++) {
+        const int y = sy > 0 ? i : H - 1 - i;
+        const int yn = sy > 0 ? i + 1 : H - 2 - i;
+        const int par = i & 1;
+        xch[par * PARSTRIDE + (w * 2 + 0) * 32 + lane] = Mst[(1 * COLS + lc0 + CPW - 1) * 32 + lane];
+        xch[par * PARSTRIDE + (w * 2 + 1) * 32 + lane] = Mst[(2 * COLS + lc0) * 32 + lane];
+        cluster.sync();
+        uint32_t carry[NR];
+        if (gcol0 > 0 && gcol0 < W1) unpack<NR>(left_x[par * PARSTRIDE], carry);
+        else {
+#pragma unroll
+            for (int r = 0; r < NR; r++) carry[r] = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < CPW; j++) {
+            if (gcol0 + j >= W1) break;
+            uint32_t Cr[NR], Sr[NR], L[NR], M[NR];
+            unpack<NR>(cq[j], Cr);
+            if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
+            if (i + 1 < H) {
+                cq[j] = __ldg(C + ((size_t)yn * W1 + gcol0 + j) * 32);
+                if (SMODE == S_ACCUM) sq[j] = S[((size_t)yn * W1 + gcol0 + j) * 32];
+            }
+            // (x, y-sy)
+            unpack<NR>(Mst[(0 * COLS + lc0 + j) * 32 + lane], M);
+            path_step<NR>(M, Cr, L, P1p, P2p, lane);
+            Mst[(0 * COLS + lc0 + j) * 32 + lane] = pack<NR>(M);
+#pragma unroll
+            for (int r = 0; r < NR; r++) Sr[r] = (SMODE == S_ACCUM) ? Sr[r] + L[r] : L[r];
+            // (x-1, y-sy): state arrives from the left neighbour column
+            {
+                uint32_t old[NR];
+                unpack<NR>(Mst[(1 * COLS + lc0 + j) * 32 + lane], old);
+#pragma unroll
+                for (int r = 0; r < NR; r++) M[r] = carry[r];
+                path_step<NR>(M, Cr, L, P1p, P2p, lane);
+                Mst[(1 * COLS + lc0 + j) * 32 + lane] = pack<NR>(M);
+#pragma unroll
+                for (int r = 0; r < NR; r++) { Sr[r] += L[r]; carry[r] = old[r]; }
+            }
+            // (x+1, y-sy): state arrives from the right neighbour column (still the old row's: ascending j)
+            {
+                if (gcol0 + j + 1 >= W1) {
+#pragma unroll
+                    for (int r = 0; r < NR; r++) M[r] = 0;
+                } else if (j + 1 < CPW) {
+                    unpack<NR>(Mst[(2 * COLS + lc0 + j + 1) * 32 + lane], M);
+                } else {
+                    unpack<NR>(right_x[par * PARSTRIDE], M);
+                }
+                path_step<NR>(M, Cr, L, P1p, P2p, lane);
+                Mst[(2 * COLS + lc0 + j) * 32 + lane] = pack<NR>(M);
+#pragma unroll
+                for (int r = 0; r < NR; r++) Sr[r] += L[r];
+            }
+            S[((size_t)y * W1 + gcol0 + j) * 32] = pack<NR>(Sr);
+        }
+    }
+    cluster.sync();   // nobody may exit while a neighbour can still read its shared memory
+}
+
+template <int NR, int CPW>
+int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
+{
+    using VT = typename Vec<NR>::T;
+    const size_t smem = ((size_t)3 * V3_NW * CPW * 32 + (size_t)2 * V3_NW * 2 * 32) * sizeof(VT);
+    auto kw = k_path_vert3<NR, CPW, S_WRITE>;
+    auto ka = k_path_vert3<NR, CPW, S_ACCUM>;
+    V3D_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    V3D_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(V3_CL * batch);
+    cfg.blockDim = dim3(V3_NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = V3_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const uint16_t* C = ctx->C;
+    uint16_t* S = ctx->S;
+    const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
+    if (!ctx->max_clusters) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kw, &cfg) == cudaSuccess) ctx->max_clusters = n;
+        else cudaGetLastError();
+    }
+    V3D_CUDA(cudaLaunchKernelEx(&cfg, accum ? ka : kw, C, S, ctx->W1, ctx->H, sy, P1p, P2p));
+    V3D_LAUNCHED(ctx, 1);
+    return V3D_OK;
+}
+
+// Returns 1 when the fused sweep ran, 0 when the shape does not fit it (caller falls back), < 0 on error.
+template <int NR>
+int try_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
+{
+    if (NR > 2 || ctx->no_fused_vertical) return 0;
+    const int need = (ctx->W1 + V3_CL * V3_NW - 1) / (V3_CL * V3_NW);
+    int rc;
+    if (need <= 2) rc = launch_vert3<(NR > 2 ? 1 : NR), 2>(ctx, batch, sy, accum, st);
+    else if (need <= 4) rc = launch_vert3<(NR > 2 ? 1 : NR), 4>(ctx, batch, sy, accum, st);
+    else if (need <= 7) rc = launch_vert3<(NR > 2 ? 1 : NR), 7>(ctx, batch, sy, accum, st);
+    else if (need <= 8) rc = launch_vert3<(NR > 2 ? 1 : NR), 8>(ctx, batch, sy, accum, st);
+    else return 0;
+    return rc ? rc : 1;
+}
+
 template <int NR>
 int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
 {
@@ -281,16 +452,24 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
     {
         V3dScope scope(ctx, ST_PATHS, st);
         // top-down sweep: predecessors (x, y-1), (x-1, y-1), (x+1, y-1)
-        k_path_vert<NR, S_WRITE, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, +1, P1p, P2p);
-        k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, +1, +1, P1p, P2p);
-        k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, -1, +1, P1p, P2p);
-        V3D_LAUNCHED(ctx, 3);
+        int fused = try_vert3<NR>(ctx, batch, +1, false, st);
+        if (fused < 0) return fused;
+        if (!fused) {
+            k_path_vert<NR, S_WRITE, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, +1, P1p, P2p);
+            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, +1, +1, P1p, P2p);
+            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, -1, +1, P1p, P2p);
+            V3D_LAUNCHED(ctx, 3);
+        }
         if (ctx->p.mode == V3D_MODE_HH) {
             // bottom-up sweep: predecessors (x, y+1), (x+1, y+1), (x-1, y+1)
-            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, -1, P1p, P2p);
-            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, -1, -1, P1p, P2p);
-            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, +1, -1, P1p, P2p);
-            V3D_LAUNCHED(ctx, 3);
+            fused = try_vert3<NR>(ctx, batch, -1, true, st);
+            if (fused < 0) return fused;
+            if (!fused) {
+                k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, -1, P1p, P2p);
+                k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, -1, -1, P1p, P2p);
+                k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, +1, -1, P1p, P2p);
+                V3D_LAUNCHED(ctx, 3);
+            }
         }
         k_path_lr<NR, S_ACCUM, PF><<<gh, block, 0, st>>>(C, S, W1, rows, P1p, P2p);
         V3D_LAUNCHED(ctx, 1);

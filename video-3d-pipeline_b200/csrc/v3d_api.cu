@@ -173,6 +173,8 @@ int v3d_destroy(v3d_ctx* ctx)
 size_t v3d_workspace_bytes(const v3d_ctx* ctx) { return ctx ? ctx->bytes : 0; }
 unsigned long long v3d_launch_count(const v3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int v3d_fused_sweep_clusters(const v3d_ctx* ctx) { return ctx ? ctx->max_clusters : 0; }
+
 int v3d_set_debug_taps(v3d_ctx* ctx, int enabled)
 {
     if (!ctx) return v3d_fail(V3D_EINVAL, "null context");

@@ -44,6 +44,8 @@ struct v3d_ctx {
     int timing;
     int debug_taps;          // keep S_total and the pre-speckle median for v3d_debug_tap
     int guided_attr_set;
+    int max_clusters;        // co-resident frame clusters of the fused vertical sweep (0 = not queried)
+    int no_fused_vertical;   // test hook: force the one-direction-per-launch path kernels
     std::vector<V3dTimedSpan> spans;
     double stage_ms[ST_COUNT];
 };

@@ -64,6 +64,8 @@ def lib():
     L.v3d_guided_upscale.argtypes = [vp, vp, i32, i32, vp, i32, i32, i32, i32, C.c_float, vp, vp, vp]
     L.v3d_depth_frames.argtypes = [vp, vp, sz, sz, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, C.c_float, vp, vp]
     L.v3d_depth_frames_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, C.c_float, vp, vp]
+    L.v3d_fused_sweep_clusters.argtypes = [vp]
+    L.v3d_fused_sweep_clusters.restype = i32
     L.v3d_launch_count.argtypes = [vp]
     L.v3d_launch_count.restype = C.c_ulonglong
     L.v3d_set_timing.argtypes = [vp, i32]
@@ -159,6 +161,10 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().v3d_launch_count(self._h))
+
+    @property
+    def fused_sweep_clusters(self):
+        return int(lib().v3d_fused_sweep_clusters(self._h))
 
     def set_timing(self, on):
         _check(lib().v3d_set_timing(self._h, int(bool(on))), "v3d_set_timing")
