@@ -50,12 +50,13 @@ CELLS = W1 * EYE_H * D
 ALG_IOPS = (31 + 9 * 5) * CELLS                          # 18.8 Gop
 
 
-def workload_config(batch, n_gpus):
+def workload_config(batch, n_gpus, lanes=1):
     return {
         "workload": "cfg2+cfg3 fused: full-SBS 3840x1080 (1920x1080/eye) SGBM numDisparities=128 MODE_SGBM "
                     "with uniqueness, sub-pixel, LR check, median, speckle -> min-max uint16 -> guided upscale "
                     "to 3840x2160 uint16 (4K RGB guide, r=8, eps=1e-3)",
         "frames_per_step_per_gpu": batch,
+        "lanes": lanes,
         "global_frames_per_step": batch * n_gpus,
         "parallelism": f"frame-range shards x{n_gpus}, no collective",
         "l2": "inputs (37.3 MB/frame) and the per-frame C/S volumes (0.99 GB/frame) exceed the 126 MB L2",
@@ -219,55 +220,100 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     B = args.batch
-    sbs_np, guide_np = synthetic_batch(B)
-    ctx = nv.Context(EYE_W, EYE_H, nv.SgbmParams(numDisparities=D, mode=nv.MODE_SGBM), max_batch=B, device=local)
-    sbs_d = torch.from_numpy(sbs_np).to(dev)
-    guide_d = torch.from_numpy(guide_np).to(dev)
-    sbs_h = torch.from_numpy(sbs_np).pin_memory()
-    guide_h = torch.from_numpy(guide_np).pin_memory()
-    out_h = torch.empty((B, GH, GW), dtype=torch.uint16).pin_memory()
+    n_lanes = max(1, min(args.lanes, B))
+    if B % n_lanes:
+        raise ValueError("--batch must be a multiple of --lanes")
+    Bl = B // n_lanes
+    sbs_np, guide_np = synthetic_batch(Bl)
+    params = nv.SgbmParams(numDisparities=D, mode=nv.MODE_SGBM)
 
-    def step_device():
-        return ctx.depth_frames(sbs_d, False, guide_d, RADIUS, EPS, want=())
+    class Lane:
+        """One stream + context + buffers; lanes overlap each other's tails, copies and kernels."""
+        def __init__(self):
+            self.stream = torch.cuda.Stream(dev)
+            self.ctx = nv.Context(EYE_W, EYE_H, params, max_batch=Bl, device=local)
+            self.sbs_d = torch.from_numpy(sbs_np).to(dev)
+            self.guide_d = torch.from_numpy(guide_np).to(dev)
+            self.sbs_h = torch.from_numpy(sbs_np).pin_memory()
+            self.guide_h = torch.from_numpy(guide_np).pin_memory()
+            self.out_h = torch.empty((Bl, GH, GW), dtype=torch.uint16).pin_memory()
 
-    def step_host():
-        ctx.depth_frames_host(sbs_h, False, guide_h, RADIUS, EPS, out={"out4k": out_h})
+        def step_device(self):
+            with torch.cuda.stream(self.stream):
+                self.ctx.depth_frames(self.sbs_d, False, self.guide_d, RADIUS, EPS, want=())
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+        def step_host(self):
+            with torch.cuda.stream(self.stream):
+                self.ctx.depth_frames_host(self.sbs_h, False, self.guide_h, RADIUS, EPS, out={"out4k": self.out_h})
+
+    lanes = [Lane() for _ in range(n_lanes)]
+    ctx = lanes[0].ctx
+
+    def launch_count():
+        return sum(l.ctx.launch_count for l in lanes)
+
+    def timed(kind, steps, warmup):
+        """K steps of every lane between two events on the default stream; lanes fork from / join into it."""
+        import threading
+
+        def run(lane, n):
+            torch.cuda.set_device(local)
+            for _ in range(n):
+                (lane.step_device if kind == "device" else lane.step_host)()
+
+        def all_lanes(n):
+            if kind == "device" or n_lanes == 1:
+                for _ in range(n):
+                    for lane in lanes:
+                        (lane.step_device if kind == "device" else lane.step_host)()
+            else:   # the host entry point is synchronous: one host thread per lane (ctypes drops the GIL)
+                th = [threading.Thread(target=run, args=(lane, n)) for lane in lanes]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+
+        all_lanes(warmup)
         barrier()
-        l0 = ctx.launch_count
+        l0 = launch_count()
+        cur = torch.cuda.current_stream(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
+        e0.record(cur)
+        for lane in lanes:
+            lane.stream.wait_event(e0)
+        all_lanes(steps)
+        for lane in lanes:
+            ev = torch.cuda.Event()
+            ev.record(lane.stream)
+            cur.wait_event(ev)
+        e1.record(cur)
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = ctx.launch_count - l0
+        launches = launch_count() - l0
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches = timed(step_device, args.steps, args.warmup)
+    ms, launches = timed("device", args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms / 1000.0)
 
-    ms_e2e, _ = timed(step_host, args.steps, max(args.warmup, 3) if args.warmup else 0)
+    ms_e2e, _ = timed("host", args.steps, max(args.warmup, 3) if args.warmup else 0)
     e2e = world * B * args.steps / (ms_e2e / 1000.0)
 
-    # per-stage breakdown (CUDA events on the launching stream), separate untimed pass
+    # per-stage breakdown (CUDA events on the launching stream) of ONE lane running alone, untimed pass
     ctx.set_timing(True)
     ctx.reset_timing()
     prof_steps = max(1, min(args.steps, 3))
     for _ in range(prof_steps):
-        step_device()
+        lanes[0].step_device()
     torch.cuda.synchronize(dev)
     stages = {k: v / prof_steps for k, v in ctx.stage_ms().items()}
     ctx.set_timing(False)
+    workspace_gb = sum(l.ctx.workspace_bytes for l in lanes) / 1e9
+    fused_clusters = ctx.fused_sweep_clusters
 
     line = None
     if rank == 0:
@@ -278,16 +324,16 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         # dominant kernel family = the path-aggregation launches (4 of them for MODE_SGBM; the 5th is in 'wta')
-        n_path_kernels = 4
+        n_path_kernels = 2      # fused vertical sweep + left-to-right pass (the right-to-left pass is 'wta')
         dom_name = max(("cost", "paths", "wta", "guided"), key=lambda k: stages.get(k, 0.0))
         dom_ms = stages[dom_name] / (n_path_kernels if dom_name == "paths" else (2 if dom_name == "guided" else 1))
-        alg_bytes = (ALG_BYTES_FUSED if dom_name == "guided" else ALG_BYTES_DEPTH) * B
+        alg_bytes = (ALG_BYTES_FUSED if dom_name == "guided" else ALG_BYTES_DEPTH) * Bl
         achieved = alg_bytes / (dom_ms / 1000.0) / 1e9
-        vol = 2.0 * CELLS * B            # one uint16 volume, bytes per launch
-        design_bytes = {"cost": vol, "paths": 3 * vol - vol / n_path_kernels, "wta": 2 * vol,
-                        "guided": (GUIDE_BYTES + 16 * GW * GH) * B}[dom_name]
+        vol = 2.0 * CELLS * Bl           # one uint16 volume, bytes per launch (one lane)
+        design_bytes = {"cost": vol, "paths": (2 * vol + 3 * vol) / 2, "wta": 2 * vol,
+                        "guided": (GUIDE_BYTES + 16 * GW * GH) * Bl}[dom_name]
         roofline = {
-            "bound": "hbm", "kernel": {"cost": "k_cost", "paths": "k_path_vert/k_path_lr (avg of 4 launches)",
+            "bound": "hbm", "kernel": {"cost": "k_cost", "paths": "k_path_vert3 + k_path_lr (avg of 2 launches)",
                                        "wta": "k_path_rl_wta", "guided": "k_guided_coeff/apply (avg of 2)"}[dom_name],
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": None, "peak_source": peak_src,
@@ -312,7 +358,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int16/f32", "data": "synthetic", "config": workload_config(B, world),
+            "vs_baseline": None, "dtype": "int16/f32", "data": "synthetic", "config": workload_config(B, world, n_lanes),
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * (SBS_BYTES + GUIDE_BYTES),
                     "d2h_bytes_per_step": B * OUT_BYTES, "ms_per_step": ms_e2e / args.steps},
@@ -320,10 +366,12 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "stages_ms_per_step": stages,
-            "workspace_gb": ctx.workspace_bytes / 1e9,
-            "fused_sweep_clusters": ctx.fused_sweep_clusters,
+            "workspace_gb": workspace_gb,
+            "fused_sweep_clusters": fused_clusters,
+            "lanes": n_lanes,
         }
-    ctx.close()
+    for lane in lanes:
+        lane.ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -337,7 +385,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=30, help="frames per step per GPU")
+    ap.add_argument("--lanes", type=int, default=2, help="streams/contexts the batch is split over")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
