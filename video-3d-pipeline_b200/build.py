@@ -12,7 +12,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "video_3d_pipeline" / "libv3d.so"
-SOURCES = ["v3d_api.cu", "k_gray.cu", "k_cost.cu", "k_paths.cu", "k_post.cu", "k_guided.cu"]
+SOURCES = ["v3d_api.cu", "k_gray.cu", "k_cost.cu", "k_paths.cu", "k_paths_h.cu", "k_post.cu", "k_guided.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--shared",
@@ -23,7 +23,7 @@ def _stale():
     if not OUT.exists():
         return True
     t = OUT.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "v3d_internal.h", HERE.parent / "include" / "v3d.h", Path(__file__)]
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "v3d_internal.h", CSRC / "path_common.cuh", HERE.parent / "include" / "v3d.h", Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 
 

@@ -11,57 +11,14 @@
 //   state kept per path:  M[d] = min(L[d] - min_d L, P2)      (the P2 clamp folds the "minL + P2" term)
 //   step:                 L[d] = C[d] + min(M[d], min(M[d-1], M[d+1]) + P1)
 // A predecessor outside the window contributes L = 0, i.e. M = 0, which is also the initial state.
-#include "v3d_internal.h"
+#include "path_common.cuh"
 
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
 namespace {
 
-template <int NR> struct Vec;
-template <> struct Vec<1> { using T = uint32_t; };
-template <> struct Vec<2> { using T = uint2; };
-template <> struct Vec<4> { using T = uint4; };
 
-template <int NR> __device__ __forceinline__ void unpack(const typename Vec<NR>::T& v, uint32_t (&r)[NR]);
-template <> __device__ __forceinline__ void unpack<1>(const uint32_t& v, uint32_t (&r)[1]) { r[0] = v; }
-template <> __device__ __forceinline__ void unpack<2>(const uint2& v, uint32_t (&r)[2]) { r[0] = v.x; r[1] = v.y; }
-template <> __device__ __forceinline__ void unpack<4>(const uint4& v, uint32_t (&r)[4]) { r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
-template <int NR> __device__ __forceinline__ typename Vec<NR>::T pack(const uint32_t (&r)[NR]);
-template <> __device__ __forceinline__ uint32_t pack<1>(const uint32_t (&r)[1]) { return r[0]; }
-template <> __device__ __forceinline__ uint2 pack<2>(const uint32_t (&r)[2]) { return make_uint2(r[0], r[1]); }
-template <> __device__ __forceinline__ uint4 pack<4>(const uint32_t (&r)[4]) { return make_uint4(r[0], r[1], r[2], r[3]); }
-
-// One step of the recurrence.  M in/out, C in, L out.  P1p / P2p are P1, P2 duplicated in both halves.
-template <int NR>
-__device__ __forceinline__ void path_step(uint32_t (&M)[NR], const uint32_t (&C)[NR], uint32_t (&L)[NR],
-                                          uint32_t P1p, uint32_t P2p, int lane)
-{
-    uint32_t up = __shfl_up_sync(V3D_FULL_MASK, M[NR - 1], 1);
-    uint32_t dn = __shfl_down_sync(V3D_FULL_MASK, M[0], 1);
-    // d = -1 and d = D do not exist: any value >= P2 is "infinity" because M <= P2 and P1 > 0
-    if (lane == 0) up = P2p;
-    if (lane == 31) dn = P2p;
-    uint32_t sh[NR + 1];
-    sh[0] = __byte_perm(up, M[0], 0x5432);            // (M[d-1] for the even d, M[d-1] for the odd d)
-#pragma unroll
-    for (int k = 1; k < NR; k++) sh[k] = __byte_perm(M[k - 1], M[k], 0x5432);
-    sh[NR] = __byte_perm(M[NR - 1], dn, 0x5432);
-    uint32_t m = 0xffffffffu;
-#pragma unroll
-    for (int k = 0; k < NR; k++) {
-        const uint32_t nb = __vminu2(sh[k], sh[k + 1]);
-        L[k] = C[k] + __viaddmin_u16x2(nb, P1p, M[k]);   // halves never carry: C + P2 < 2^15
-        m = __vminu2(m, L[k]);
-    }
-    m = __vminu2(m, __byte_perm(m, 0, 0x1032));          // both halves = this lane's minimum
-    const uint32_t mm = __reduce_min_sync(V3D_FULL_MASK, m);
-    const uint32_t neg = ((0x10000u - (mm & 0xffffu)) & 0xffffu) * 0x10001u;
-#pragma unroll
-    for (int k = 0; k < NR; k++) M[k] = __viaddmin_s16x2(L[k], neg, P2p);
-}
-
-enum { S_WRITE = 0, S_ACCUM = 1 };
 
 // ------------------------------------------------------------------------------------------
 // Vertical / diagonal directions.  sx = x step along the path (-dx), sy = y step (-dy).
@@ -471,6 +428,10 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
                 V3D_LAUNCHED(ctx, 3);
             }
         }
+    }
+    if (!ctx->no_tma_rows) return v3d_launch_paths_horizontal(ctx, batch, st);
+    {
+        V3dScope scope(ctx, ST_PATHS, st);
         k_path_lr<NR, S_ACCUM, PF><<<gh, block, 0, st>>>(C, S, W1, rows, P1p, P2p);
         V3D_LAUNCHED(ctx, 1);
     }

@@ -45,7 +45,9 @@ struct v3d_ctx {
     int debug_taps;          // keep S_total and the pre-speckle median for v3d_debug_tap
     int guided_attr_set;
     int max_clusters;        // co-resident frame clusters of the fused vertical sweep (0 = not queried)
-    int no_fused_vertical;   // test hook: force the one-direction-per-launch path kernels
+    int no_fused_vertical;
+    int no_tma_rows;         // test hook: register-prefetch horizontal kernels instead of the TMA-staged ones
+    int h_attr_set;   // test hook: force the one-direction-per-launch path kernels
     std::vector<V3dTimedSpan> spans;
     double stage_ms[ST_COUNT];
 };
@@ -75,6 +77,7 @@ int v3d_launch_prefilter(v3d_ctx* ctx, const uint8_t* left, const uint8_t* right
 int v3d_launch_cost(v3d_ctx* ctx, int batch, cudaStream_t st);
 // k_paths.cu
 int v3d_launch_paths(v3d_ctx* ctx, int batch, cudaStream_t st);
+int v3d_launch_paths_horizontal(v3d_ctx* ctx, int batch, cudaStream_t st);
 // k_post.cu
 int v3d_launch_select(v3d_ctx* ctx, int batch, cudaStream_t st);
 int v3d_launch_median(v3d_ctx* ctx, int batch, int16_t* dst, size_t dpitch, size_t dstride, cudaStream_t st);
