@@ -75,17 +75,30 @@ struct CostSmem {
 
 __device__ __forceinline__ uint32_t neg16(uint32_t v) { return (0x10000u - v) & 0xffffu; }
 
+// Row staging is split in two so that the global load of row r+2 is in flight while row r is being
+// computed: stage_load() only issues the load, stage_store() (one iteration later) expands the record
+// into the shared-memory layout.
 template <int NR, int R>
-__device__ __forceinline__ void stage_row(CostSmem<NR, R>& sm, int buf, const uint2* __restrict__ pfL,
-                                          const uint2* __restrict__ pfR, int W, int xs, int tid)
+__device__ __forceinline__ uint2 stage_load(const uint2* __restrict__ pfL, const uint2* __restrict__ pfR, int W, int xs,
+                                            int tid)
+{
+    constexpr int D = 64 * NR;
+    constexpr int NE = TXW + D - 1;
+    if (tid < NE) {
+        const int Xhi = xs - R + (TXW - 1) + D;
+        return __ldg(pfR + min(max(Xhi - tid, 0), W - 1));
+    }
+    if (tid < NE + TXW) return __ldg(pfL + min(max(xs - R + (tid - NE) + D, 0), W - 1));
+    return make_uint2(0, 0);
+}
+
+template <int NR, int R>
+__device__ __forceinline__ void stage_store(CostSmem<NR, R>& sm, int buf, const uint2 rec, int tid)
 {
     constexpr int D = 64 * NR;
     constexpr int NE = TXW + D - 1;
     if (tid < NE) {
         const int q = tid;
-        const int Xhi = xs - R + (TXW - 1) + D;
-        const int xr = min(max(Xhi - q, 0), W - 1);
-        const uint2 rec = __ldg(pfR + xr);
         uint16_t* base = reinterpret_cast<uint16_t*>(&sm.rbuf[buf][0][0][0]);
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
@@ -104,8 +117,6 @@ __device__ __forceinline__ void stage_row(CostSmem<NR, R>& sm, int buf, const ui
         }
     } else if (tid < NE + TXW) {
         const int c = tid - NE;
-        const int X = min(max(xs - R + c + D, 0), W - 1);
-        const uint2 rec = __ldg(pfL + X);
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
             const uint32_t w = ch ? rec.y : rec.x;
@@ -149,10 +160,13 @@ k_cost(const uint2* __restrict__ pfL, const uint2* __restrict__ pfR, uint32_t* _
         for (int i = 0; i < K; i++) ring[i][k] = 0;
     }
 
-    {
-        const int rr = min(max(ystart, 0), H - 1);
-        stage_row<NR, R>(sm, 0, pfL + (size_t)rr * W, pfR + (size_t)rr * W, W, xs, tid);
-    }
+    auto load_row = [&](int r) -> uint2 {
+        const int rr = min(max(r, 0), H - 1);
+        return stage_load<NR, R>(pfL + (size_t)rr * W, pfR + (size_t)rr * W, W, xs, tid);
+    };
+    uint2 rec = load_row(ystart);
+    stage_store<NR, R>(sm, 0, rec, tid);
+    rec = load_row(ystart + 1);
     __syncthreads();
 
     for (int row = ystart; row < yend; row += K) {
@@ -162,8 +176,8 @@ k_cost(const uint2* __restrict__ pfL, const uint2* __restrict__ pfR, uint32_t* _
             if (r >= yend) break;
             const int cur = (r - ystart) & 1;
             if (r + 1 < yend) {
-                const int rr = min(max(r + 1, 0), H - 1);
-                stage_row<NR, R>(sm, cur ^ 1, pfL + (size_t)rr * W, pfR + (size_t)rr * W, W, xs, tid);
+                stage_store<NR, R>(sm, cur ^ 1, rec, tid);    // row r+1, loaded one iteration ago
+                rec = load_row(r + 2);                        // in flight while row r is computed
             }
             if (valid_col) {
                 const uint4 ls = sm.lbuf[cur][c][0];

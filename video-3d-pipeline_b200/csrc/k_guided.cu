@@ -66,10 +66,10 @@ k_guided_coeff(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* 
 {
     extern __shared__ float4 gsm[];
     const int r = RT > 0 ? RT : r_arg;
-    const int RW = GT + 2 * r, RH = GT + 2 * r, BP = RW + 1;          // base pitch (float4), odd -> conflict free
+    const int RW = GT + 2 * r, RH = GT + 2 * r, BP = RW + 1;          // base pitch (8-byte entries), odd
     const int HP = GT + 1;
-    float4* base = gsm;                                                 // [RH][BP]
-    float* hs = reinterpret_cast<float*>(gsm + (size_t)RH * BP);       // [13][RH][HP]
+    uint2* base = reinterpret_cast<uint2*>(gsm);                       // [RH][BP] {rgb bytes, p - centre}
+    float* hs = reinterpret_cast<float*>(base + (size_t)RH * BP);      // [13][RH][HP]
     __shared__ TileTaps tp;
     __shared__ float4 centre;
     const int tid = threadIdx.x;
@@ -89,8 +89,9 @@ k_guided_coeff(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* 
         axis_tap(Y, h, gh, tp.y0[j], tp.y1[j], tp.fy[j]);
     }
     __syncthreads();
-    auto sample = [&](int t, int j) -> float4 {
-        const float3 I = load_guide(guide, gw, tp.gx[t], tp.gy[j]);
+    auto sample = [&](int t, int j, uint32_t& rgb) -> float {
+        const uint8_t* gp = guide + ((size_t)tp.gy[j] * gw + tp.gx[t]) * 3;
+        rgb = (uint32_t)__ldg(gp) | ((uint32_t)__ldg(gp + 1) << 8) | ((uint32_t)__ldg(gp + 2) << 16);
         const float s = 1.0f / 65535.0f;
         const uint16_t* r0 = depth + (size_t)tp.y0[j] * w;
         const uint16_t* r1 = depth + (size_t)tp.y1[j] * w;
@@ -99,29 +100,39 @@ k_guided_coeff(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* 
         const float p10 = __ldg(r1 + tp.x0[t]) * s, p11 = __ldg(r1 + tp.x1[t]) * s;
         const float top = p00 * (1.0f - fx) + p01 * fx;
         const float bot = p10 * (1.0f - fx) + p11 * fx;
-        return make_float4(I.x, I.y, I.z, top * (1.0f - fy) + bot * fy);
+        return top * (1.0f - fy) + bot * fy;
     };
+    const float k255 = 1.0f / 255.0f;
     // per-tile centre: moments are taken about it (box sums are shift covariant)
-    if (tid == 0) centre = sample(min(r + GT / 2, RW - 1), min(r + GT / 2, RH - 1));
+    if (tid == 0) {
+        uint32_t rgb;
+        const float p = sample(min(r + GT / 2, RW - 1), min(r + GT / 2, RH - 1), rgb);
+        centre = make_float4((rgb & 0xff) * k255, ((rgb >> 8) & 0xff) * k255, ((rgb >> 16) & 0xff) * k255, p);
+    }
     __syncthreads();
     const float4 cc = centre;
     for (int i = tid; i < RW * RH; i += 256) {
         const int j = i / RW, t = i - j * RW;
-        const float4 v = sample(t, j);
-        base[j * BP + t] = make_float4(v.x - cc.x, v.y - cc.y, v.z - cc.z, v.w - cc.w);
+        uint32_t rgb;
+        const float p = sample(t, j, rgb);
+        base[j * BP + t] = make_uint2(rgb, __float_as_uint(p - cc.w));
     }
     __syncthreads();
+    auto tap = [&](const uint2 e) -> float4 {     // centred (I, p) of one region pixel
+        return make_float4(fmaf((float)(e.x & 0xff), k255, -cc.x), fmaf((float)((e.x >> 8) & 0xff), k255, -cc.y),
+                           fmaf((float)((e.x >> 16) & 0xff), k255, -cc.z), __uint_as_float(e.y));
+    };
 
     // horizontal box sums: item = (row j, run of GRUN output columns); first output direct, rest slid
     for (int it = tid; it < RH * (GT / GRUN); it += 256) {
         const int j = it % RH, g = it / RH;
-        const float4* row = base + j * BP + g * GRUN;
+        const uint2* row = base + j * BP + g * GRUN;
         float acc[13], m[13];
 #pragma unroll
         for (int q = 0; q < 13; q++) acc[q] = 0.0f;
 #pragma unroll 1
         for (int t = 0; t <= 2 * r; t++) {
-            moments13(row[t], m);
+            moments13(tap(row[t]), m);
 #pragma unroll
             for (int q = 0; q < 13; q++) acc[q] += m[q];
         }
@@ -130,10 +141,10 @@ k_guided_coeff(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* 
         for (int q = 0; q < 13; q++) out[(size_t)q * RH * HP] = acc[q];
 #pragma unroll 1
         for (int o = 1; o < GRUN; o++) {
-            moments13(row[o + 2 * r], m);
+            moments13(tap(row[o + 2 * r]), m);
 #pragma unroll
             for (int q = 0; q < 13; q++) acc[q] += m[q];
-            moments13(row[o - 1], m);
+            moments13(tap(row[o - 1]), m);
 #pragma unroll
             for (int q = 0; q < 13; q++) acc[q] -= m[q];
 #pragma unroll
@@ -249,7 +260,7 @@ k_guided_apply(const float4* __restrict__ ab, const uint8_t* __restrict__ guide,
 
 constexpr size_t sm_coeff_max()
 {
-    return (size_t)(GT + 2 * GRMAX) * (GT + 2 * GRMAX + 1) * 16 + (size_t)13 * (GT + 2 * GRMAX) * (GT + 1) * 4;
+    return (size_t)(GT + 2 * GRMAX) * (GT + 2 * GRMAX + 1) * 8 + (size_t)13 * (GT + 2 * GRMAX) * (GT + 1) * 4;
 }
 constexpr size_t sm_apply_max()
 {
@@ -261,7 +272,7 @@ int launch_guided_rt(v3d_ctx* ctx, const uint16_t* depth, int w, int h, const ui
                      int batch, int r, float eps, uint16_t* out, float* q, cudaStream_t st)
 {
     const int RW = GT + 2 * r;
-    const size_t sm_coeff = (size_t)RW * (RW + 1) * sizeof(float4) + (size_t)13 * RW * (GT + 1) * sizeof(float);
+    const size_t sm_coeff = (size_t)RW * (RW + 1) * sizeof(uint2) + (size_t)13 * RW * (GT + 1) * sizeof(float);
     const size_t sm_apply = (size_t)RW * (RW + 1) * sizeof(float4) + (size_t)RW * (GT + 1) * sizeof(float4);
     if (!(ctx->guided_attr_set & (1 << RT))) {
         V3D_CUDA(cudaFuncSetAttribute(k_guided_coeff<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_coeff_max()));
