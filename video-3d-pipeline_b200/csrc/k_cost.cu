@@ -2,14 +2,25 @@
 // Birchfield-Tomasi cost volume C[b][y][x][d] (uint16, d fastest, x in window coordinates).
 // Replaces the first third of cv2.StereoSGBM.compute (depth.py:341): OpenCV calcPixelCostBT plus the
 // blockSize x blockSize box sum of computeDisparitySGBM.  Spec: SURVEY.md Appendix A.2.
+//
+// Two kernels:
+//   k_prefilter_expand  writes, once per pixel, the operands of the BT cost in the exact layout the cost
+//                       kernel's lanes consume them (packed int16 pairs, right image column-reversed, both
+//                       pair alignments), so that
+//   k_cost              stages a row with five cp.async.bulk copies (TMA, mbarrier-completed, 3 rows deep)
+//                       and spends its instructions on the cost arithmetic only.
 #include "v3d_internal.h"
+#include "tma.cuh"
 
 namespace {
 
+constexpr int TXW = 16;       // window columns per block (one warp each); TXW - 2R of them are output columns
+constexpr int PADL = 32;      // front padding (elements) of the reversed right-image rows
+
 // ---------------------------------------------------------------------------------------------
-// Prefilter: one uint2 record per pixel  {x: sobel v | lo<<8 | hi<<16,  y: intensity v | lo<<8 | hi<<16}
+// Prefilter record of one pixel: {x: sobel v | lo<<8 | hi<<16,  y: intensity v | lo<<8 | hi<<16}
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int gray_at(const uint8_t* img, size_t pitch, int W, int H, int x, int y)
+__device__ __forceinline__ int gray_at(const uint8_t* img, size_t pitch, int H, int x, int y)
 {
     return __ldg(img + (size_t)min(max(y, 0), H - 1) * pitch + x);
 }
@@ -18,28 +29,22 @@ __device__ __forceinline__ void prefilter_px(const uint8_t* img, size_t pitch, i
                                              int ftzero, int& sob, int& inten)
 {
     if (x <= 0 || x >= W - 1) { sob = ftzero; inten = ftzero; return; }   // border fill hits both channels
-    const int g = 2 * (gray_at(img, pitch, W, H, x + 1, y) - gray_at(img, pitch, W, H, x - 1, y)) +
-                  (gray_at(img, pitch, W, H, x + 1, y - 1) - gray_at(img, pitch, W, H, x - 1, y - 1)) +
-                  (gray_at(img, pitch, W, H, x + 1, y + 1) - gray_at(img, pitch, W, H, x - 1, y + 1));
+    const int g = 2 * (gray_at(img, pitch, H, x + 1, y) - gray_at(img, pitch, H, x - 1, y)) +
+                  (gray_at(img, pitch, H, x + 1, y - 1) - gray_at(img, pitch, H, x - 1, y - 1)) +
+                  (gray_at(img, pitch, H, x + 1, y + 1) - gray_at(img, pitch, H, x - 1, y + 1));
     sob = min(max(g, -ftzero), ftzero) + ftzero;
-    inten = gray_at(img, pitch, W, H, x, y);
+    inten = gray_at(img, pitch, H, x, y);
 }
 
-__global__ void __launch_bounds__(256)
-k_prefilter(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, size_t gpitch, size_t gstride,
-            int W, int H, int ftzero, uint2* __restrict__ pfL, uint2* __restrict__ pfR)
+__device__ __forceinline__ uint2 prefilter_rec(const uint8_t* img, size_t pitch, int W, int H, int x, int y, int ftzero)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    const int eye = blockIdx.z & 1, b = blockIdx.z >> 1;
-    if (x >= W) return;
-    const uint8_t* img = (eye ? right : left) + (size_t)b * gstride;
+    if (x < 0 || x >= W) return make_uint2(0, 0);
     int s[3], t[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int xx = x - 1 + i;
         if (xx < 0 || xx >= W) { s[i] = -1; t[i] = -1; }     // missing neighbour
-        else prefilter_px(img, gpitch, W, H, xx, y, ftzero, s[i], t[i]);
+        else prefilter_px(img, pitch, W, H, xx, y, ftzero, s[i], t[i]);
     }
     auto interval = [](const int (&p)[3]) -> uint32_t {
         const int v = p[1];
@@ -48,93 +53,77 @@ k_prefilter(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right,
         const int lo = min(v, min(l, r)), hi = max(v, max(l, r));
         return (uint32_t)v | ((uint32_t)lo << 8) | ((uint32_t)hi << 16);
     };
-    uint2 rec = make_uint2(interval(s), interval(t));
-    (eye ? pfR : pfL)[((size_t)b * H + y) * W + x] = rec;
+    return make_uint2(interval(s), interval(t));
 }
-
-// ---------------------------------------------------------------------------------------------
-// Cost volume.  Block = a strip of TXW window columns (one warp per column, TX = TXW-2R of them are
-// output columns, the rest are halo) sweeping a band of rows top-down.
-//   lane l owns the disparity pairs d = 2l + 64k (+1), k < NR        (D = 64*NR)
-//   vertical (2R+1)-row sum: sliding window in registers (ring of 2R+1 packed pix values)
-//   horizontal (2R+1)-column sum: through shared memory, clamped in WINDOW coordinates
-// The right-image row segment the strip needs is staged once per row into shared memory as packed
-// int16 {v, -v, lo, -hi} quads in reversed column order, in two copies (even / odd start) so every
-// lane's 128-bit load is aligned whatever the column parity.
-// ---------------------------------------------------------------------------------------------
-constexpr int TXW = 16;
-
-template <int NR, int R>
-struct CostSmem {
-    static constexpr int D = 64 * NR;
-    static constexpr int NWORDS = D / 2 + 8;
-    uint4 rbuf[2][2][2][NWORDS];   // [row parity][channel][copy][word] = {v, -v, lo, -hi} pairs
-    uint4 lbuf[2][TXW][2];         // [row parity][column][channel]   = {u, -u, lo, -hi} duplicated in both halves
-    uint32_t vbuf[2][TXW][D / 2];  // [row parity][column][pair]      = vertical sums
-};
 
 __device__ __forceinline__ uint32_t neg16(uint32_t v) { return (0x10000u - v) & 0xffffu; }
 
-// Row staging is split in two so that the global load of row r+2 is in flight while row r is being
-// computed: stage_load() only issues the load, stage_store() (one iteration later) expands the record
-// into the shared-memory layout.
-template <int NR, int R>
-__device__ __forceinline__ uint2 stage_load(const uint2* __restrict__ pfL, const uint2* __restrict__ pfR, int W, int xs,
-                                            int tid)
+// {v, -v, lo, -hi} of two elements packed as int16 pairs (e0 in the low halves)
+__device__ __forceinline__ uint4 pack_quads(uint32_t w0, uint32_t w1)
 {
-    constexpr int D = 64 * NR;
-    constexpr int NE = TXW + D - 1;
-    if (tid < NE) {
-        const int Xhi = xs - R + (TXW - 1) + D;
-        return __ldg(pfR + min(max(Xhi - tid, 0), W - 1));
-    }
-    if (tid < NE + TXW) return __ldg(pfL + min(max(xs - R + (tid - NE) + D, 0), W - 1));
-    return make_uint2(0, 0);
+    const uint32_t v0 = w0 & 0xff, l0 = (w0 >> 8) & 0xff, h0 = (w0 >> 16) & 0xff;
+    const uint32_t v1 = w1 & 0xff, l1 = (w1 >> 8) & 0xff, h1 = (w1 >> 16) & 0xff;
+    return make_uint4(v0 | (v1 << 16), neg16(v0) | (neg16(v1) << 16), l0 | (l1 << 16), neg16(h0) | (neg16(h1) << 16));
 }
 
-template <int NR, int R>
-__device__ __forceinline__ void stage_store(CostSmem<NR, R>& sm, int buf, const uint2 rec, int tid)
+// Right image: rexp[b][y][ch][cp][w] (uint4) = quads of the reversed-order elements (2w+cp, 2w+cp+1), where
+//              element e <-> image column W-1-(e-PADL).
+// Left image:  lexp[b][y][X][ch] (uint4) = {u, -u, lo, -hi} duplicated in both halves, X < W + TXW (clamped).
+__global__ void __launch_bounds__(256)
+k_prefilter_expand(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, size_t gpitch, size_t gstride,
+                   int W, int H, int ftzero, uint4* __restrict__ rexp, int wpw, uint4* __restrict__ lexp)
 {
-    constexpr int D = 64 * NR;
-    constexpr int NE = TXW + D - 1;
-    if (tid < NE) {
-        const int q = tid;
-        uint16_t* base = reinterpret_cast<uint16_t*>(&sm.rbuf[buf][0][0][0]);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (t < wpw) {
+        const uint8_t* img = right + (size_t)b * gstride;
+        const int xr0 = W - 1 - (2 * t - PADL);                    // column of element 2t
+        uint2 rec[3];
 #pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-            const uint32_t w = ch ? rec.y : rec.x;
-            const uint32_t v = w & 0xff, lo = (w >> 8) & 0xff, hi = (w >> 16) & 0xff;
-            const uint16_t q4[4] = { (uint16_t)v, (uint16_t)neg16(v), (uint16_t)lo, (uint16_t)neg16(hi) };
-            // copy 0 (even start): element q;  copy 1 (odd start): element q-1
-#pragma unroll
-            for (int cp = 0; cp < 2; cp++) {
-                const int e = q - cp;
-                if (e < 0) continue;
-                uint16_t* p = base + ((size_t)(ch * 2 + cp) * CostSmem<NR, R>::NWORDS + (e >> 1)) * 8 + (e & 1);
-#pragma unroll
-                for (int k = 0; k < 4; k++) p[2 * k] = q4[k];
-            }
-        }
-    } else if (tid < NE + TXW) {
-        const int c = tid - NE;
-#pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-            const uint32_t w = ch ? rec.y : rec.x;
-            const uint32_t v = w & 0xff, lo = (w >> 8) & 0xff, hi = (w >> 16) & 0xff;
-            sm.lbuf[buf][c][ch] = make_uint4(v * 0x10001u, neg16(v) * 0x10001u, lo * 0x10001u, neg16(hi) * 0x10001u);
-        }
+        for (int i = 0; i < 3; i++) rec[i] = prefilter_rec(img, gpitch, W, H, xr0 - i, y, ftzero);
+        uint4* base = rexp + ((size_t)(b * H + y) * 4) * wpw + t;
+        base[0 * (size_t)wpw] = pack_quads(rec[0].x, rec[1].x);    // channel 0 (sobel), copy 0: elements 2t, 2t+1
+        base[1 * (size_t)wpw] = pack_quads(rec[1].x, rec[2].x);    // channel 0, copy 1: elements 2t+1, 2t+2
+        base[2 * (size_t)wpw] = pack_quads(rec[0].y, rec[1].y);    // channel 1 (intensity)
+        base[3 * (size_t)wpw] = pack_quads(rec[1].y, rec[2].y);
+    }
+    if (t < W + TXW) {
+        const uint8_t* img = left + (size_t)b * gstride;
+        const uint2 rec = prefilter_rec(img, gpitch, W, H, min(t, W - 1), y, ftzero);
+        uint4* o = lexp + ((size_t)(b * H + y) * (W + TXW) + t) * 2;
+        o[0] = pack_quads(rec.x, rec.x);
+        o[1] = pack_quads(rec.y, rec.y);
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Cost volume.  Block = a strip of TXW window columns (one warp per column) sweeping a band of rows.
+//   lane l owns the disparity pairs d = 2l + 64k (+1), k < NR        (D = 64*NR)
+//   vertical (2R+1)-row sum: sliding window in registers (ring of 2R+1 packed pix values)
+//   horizontal (2R+1)-column sum: through shared memory, clamped in WINDOW coordinates
+// ---------------------------------------------------------------------------------------------
+constexpr int CNST = 3;       // staged rows in flight
+
+template <int NR>
+struct CostSmem {
+    static constexpr int D = 64 * NR;
+    static constexpr int NWORDS = D / 2 + 10;
+    uint4 rbuf[CNST][2][2][NWORDS];   // [stage][channel][copy][word] = {v, -v, lo, -hi} pairs of the right image
+    uint4 lbuf[CNST][TXW][2];         // [stage][column][channel]     = {u, -u, lo, -hi} of the left image
+    uint32_t vbuf[2][TXW][D / 2];     // [row parity][column][pair]   = vertical sums
+    uint64_t bar[CNST];
+};
 
 template <int NR, int R>
 __global__ void __launch_bounds__(TXW * 32)
-k_cost(const uint2* __restrict__ pfL, const uint2* __restrict__ pfR, uint32_t* __restrict__ C,
+k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, uint32_t* __restrict__ C,
        int W, int H, int W1, int band_h)
 {
     constexpr int D = 64 * NR;
     constexpr int K = 2 * R + 1;
     constexpr int TX = TXW - 2 * R;
-    __shared__ CostSmem<NR, R> sm;
+    constexpr int NWORDS = CostSmem<NR>::NWORDS;
+    __shared__ __align__(128) CostSmem<NR> sm;
 
     const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;
     const int b = blockIdx.z;
@@ -144,12 +133,39 @@ k_cost(const uint2* __restrict__ pfL, const uint2* __restrict__ pfR, uint32_t* _
     const bool inner = (c >= R && c < TXW - R && x < W1);
     const int y0 = blockIdx.y * band_h, y1 = min(H, y0 + band_h);
     const int ystart = y0 - R, yend = y1 + R;
-    pfL += (size_t)b * H * W;
-    pfR += (size_t)b * H * W;
 
-    const int q0 = TXW - 1 - c;
-    const int copy = q0 & 1;
-    const int wbase = (q0 - copy) >> 1;
+    // reversed element index of the strip's right-most image column, and the first staged word of each copy
+    const int Xhi = xs - R + (TXW - 1) + D;
+    const int gbase = (W - 1 - Xhi) + PADL;
+    const int wlo0 = gbase >> 1, wlo1 = (gbase - 1) >> 1;
+    // this warp's first element, its pair alignment and its first word inside the staged copy
+    const int e0 = gbase + (TXW - 1 - c);
+    const int copy = e0 & 1;
+    const int wrel = ((e0 - copy) >> 1) - (copy ? wlo1 : wlo0);
+    const int Xl0 = xs - R + D;                     // image column of warp 0 in the left image
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < CNST; s++) mbar_init(&sm.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int r) {                       // thread 0 only: stage image row clamp(r) for sweep row r
+        const int st = (r - ystart) % CNST;
+        const int rr = min(max(r, 0), H - 1);
+        const uint4* rrow = rexp + ((size_t)(b * H + rr) * 4) * wpw;
+        constexpr uint32_t RB = NWORDS * 16, LB = TXW * 2 * 16;
+        mbar_expect_tx(&sm.bar[st], 4 * RB + LB);
+        bulk_g2s(&sm.rbuf[st][0][0][0], rrow + 0 * (size_t)wpw + wlo0, RB, &sm.bar[st]);
+        bulk_g2s(&sm.rbuf[st][0][1][0], rrow + 1 * (size_t)wpw + wlo1, RB, &sm.bar[st]);
+        bulk_g2s(&sm.rbuf[st][1][0][0], rrow + 2 * (size_t)wpw + wlo0, RB, &sm.bar[st]);
+        bulk_g2s(&sm.rbuf[st][1][1][0], rrow + 3 * (size_t)wpw + wlo1, RB, &sm.bar[st]);
+        bulk_g2s(&sm.lbuf[st][0][0], lexp + ((size_t)(b * H + rr) * (W + TXW) + Xl0) * 2, LB, &sm.bar[st]);
+    };
+    if (tid == 0) {
+        issue(ystart);
+        if (ystart + 1 < yend) issue(ystart + 1);
+    }
 
     uint32_t ring[K][NR];
     uint32_t V[NR];
@@ -159,34 +175,30 @@ k_cost(const uint2* __restrict__ pfL, const uint2* __restrict__ pfR, uint32_t* _
 #pragma unroll
         for (int i = 0; i < K; i++) ring[i][k] = 0;
     }
+    int nb_off[K];                                  // neighbour columns, clamped in WINDOW coordinates
+#pragma unroll
+    for (int dx = -R; dx <= R; dx++) nb_off[dx + R] = (min(max(x + dx, 0), W1 - 1) - (xs - R)) * (D / 2) + lane;
+    uint32_t* out_col = C + (((size_t)b * H) * W1 + x) * (D / 2) + lane;
+    const size_t out_row = (size_t)W1 * (D / 2);
 
-    auto load_row = [&](int r) -> uint2 {
-        const int rr = min(max(r, 0), H - 1);
-        return stage_load<NR, R>(pfL + (size_t)rr * W, pfR + (size_t)rr * W, W, xs, tid);
-    };
-    uint2 rec = load_row(ystart);
-    stage_store<NR, R>(sm, 0, rec, tid);
-    rec = load_row(ystart + 1);
-    __syncthreads();
-
+    int st = 0, cur = 0;
+    uint32_t phase = 0;
     for (int row = ystart; row < yend; row += K) {
 #pragma unroll
         for (int ph = 0; ph < K; ph++) {
             const int r = row + ph;
             if (r >= yend) break;
-            const int cur = (r - ystart) & 1;
-            if (r + 1 < yend) {
-                stage_store<NR, R>(sm, cur ^ 1, rec, tid);    // row r+1, loaded one iteration ago
-                rec = load_row(r + 2);                        // in flight while row r is computed
-            }
+            mbar_wait(&sm.bar[st], phase);
             if (valid_col) {
-                const uint4 ls = sm.lbuf[cur][c][0];
-                const uint4 li = sm.lbuf[cur][c][1];
+                const uint4 ls = sm.lbuf[st][c][0];
+                const uint4 li = sm.lbuf[st][c][1];
+                const uint4* rs_p = &sm.rbuf[st][0][copy][wrel + lane];
+                const uint4* ri_p = &sm.rbuf[st][1][copy][wrel + lane];
+                uint32_t* v_p = &sm.vbuf[cur][c][lane];
 #pragma unroll
                 for (int k = 0; k < NR; k++) {
-                    const int w = wbase + lane + 32 * k;
-                    const uint4 rs = sm.rbuf[cur][0][copy][w];
-                    const uint4 ri = sm.rbuf[cur][1][copy][w];
+                    const uint4 rs = rs_p[32 * k];
+                    const uint4 ri = ri_p[32 * k];
                     // {x: v, y: -v, z: lo, w: -hi}
                     uint32_t c0 = __vimax_s16x2_relu(__vadd2(ls.x, rs.w), __vadd2(rs.z, ls.y));
                     uint32_t c1 = __vimax_s16x2_relu(__vadd2(rs.x, ls.w), __vadd2(ls.z, rs.y));
@@ -197,24 +209,25 @@ k_cost(const uint2* __restrict__ pfL, const uint2* __restrict__ pfR, uint32_t* _
                     const uint32_t pix = bs + ((bi >> 2) & 0x3fff3fffu);
                     V[k] = V[k] + pix - ring[ph][k];     // halves never borrow: V includes ring[ph]
                     ring[ph][k] = pix;
-                    sm.vbuf[cur][c][lane + 32 * k] = V[k];
+                    v_p[32 * k] = V[k];
                 }
             }
-            __syncthreads();
+            __syncthreads();        // vbuf[cur] complete; every thread is done with the previous row's stage
+            if (tid == 0 && r + 2 < yend) issue(r + 2);     // refills the stage the previous row used
             const int yo = r - R;
             if (inner && yo >= y0) {
-                uint32_t* out = C + (((size_t)b * H + yo) * W1 + x) * (D / 2);
+                const uint32_t* vb = &sm.vbuf[cur][0][0];
+                uint32_t* out = out_col + (size_t)yo * out_row;
 #pragma unroll
                 for (int k = 0; k < NR; k++) {
                     uint32_t acc = 0;
 #pragma unroll
-                    for (int dx = -R; dx <= R; dx++) {
-                        const int cn = min(max(x + dx, 0), W1 - 1) - (xs - R);
-                        acc += sm.vbuf[cur][cn][lane + 32 * k];
-                    }
-                    out[lane + 32 * k] = acc;
+                    for (int dx = 0; dx < K; dx++) acc += vb[nb_off[dx] + 32 * k];
+                    out[32 * k] = acc;
                 }
             }
+            cur ^= 1;
+            if (++st == CNST) { st = 0; phase ^= 1; }
         }
     }
 }
@@ -223,14 +236,13 @@ template <int NR>
 int launch_cost_r(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     const int band_h = 128;
-    const uint2 *pfL = ctx->pfL, *pfR = ctx->pfR;
     uint32_t* C = reinterpret_cast<uint32_t*>(ctx->C);
     const int W = ctx->W, H = ctx->H, W1 = ctx->W1;
     dim3 block(TXW * 32);
 #define V3D_COST_CASE(RR)                                                                              \
     case RR: {                                                                                         \
         dim3 grid((W1 + (TXW - 2 * RR) - 1) / (TXW - 2 * RR), (H + band_h - 1) / band_h, batch);        \
-        k_cost<NR, RR><<<grid, block, 0, st>>>(pfL, pfR, C, W, H, W1, band_h);                          \
+        k_cost<NR, RR><<<grid, block, 0, st>>>(ctx->rexp, ctx->rexp_wpw, ctx->lexp, C, W, H, W1, band_h); \
         break;                                                                                         \
     }
     switch (ctx->R) {
@@ -247,12 +259,19 @@ int launch_cost_r(v3d_ctx* ctx, int batch, cudaStream_t st)
 
 }  // namespace
 
+// words per (row, channel, copy) of the expanded right image: the row itself, the front padding and room
+// for the widest staged copy (D = 256) to read past the last column
+int v3d_rexp_words(int W) { return (W + PADL) / 2 + 160; }
+int v3d_lexp_cols(int W) { return W + TXW; }
+
 int v3d_launch_prefilter(v3d_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t gpitch,
                          size_t gstride, int batch, cudaStream_t st)
 {
     V3dScope scope(ctx, ST_PREFILTER, st);
-    dim3 grid((ctx->W + 255) / 256, ctx->H, batch * 2);
-    k_prefilter<<<grid, 256, 0, st>>>(left, right, gpitch, gstride, ctx->W, ctx->H, ctx->ftzero, ctx->pfL, ctx->pfR);
+    const int n = ctx->rexp_wpw > ctx->W + TXW ? ctx->rexp_wpw : ctx->W + TXW;
+    dim3 grid((n + 255) / 256, ctx->H, batch);
+    k_prefilter_expand<<<grid, 256, 0, st>>>(left, right, gpitch, gstride, ctx->W, ctx->H, ctx->ftzero, ctx->rexp,
+                                             ctx->rexp_wpw, ctx->lexp);
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }

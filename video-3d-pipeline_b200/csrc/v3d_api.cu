@@ -80,7 +80,7 @@ void v3d_default_params(v3d_sgbm_params* p)
 
 static void free_all(v3d_ctx* c)
 {
-    void* ptrs[] = { c->grayL, c->grayR, c->pfL, c->pfR, c->C, c->S, c->rec, c->raw, c->med, c->disp, c->labels,
+    void* ptrs[] = { c->grayL, c->grayR, c->rexp, c->lexp, c->C, c->S, c->rec, c->raw, c->med, c->disp, c->labels,
                      c->sizes, c->minmax, c->f32_tmp, c->u16_tmp, c->ab, c->in_dev, c->guide_dev, c->out_dev };
     for (void* p : ptrs) if (p) cudaFree(p);
 }
@@ -132,12 +132,14 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     c->ftzero = ftzero;
     c->gpitch = ((size_t)eye_w + 127) / 128 * 128;
     c->last_batch = 0;
+    c->rexp_wpw = v3d_rexp_words(eye_w);
 
     const size_t B = (size_t)max_batch, npx = (size_t)eye_w * eye_h;
     const size_t vol = B * (size_t)eye_h * c->W1 * c->D * sizeof(uint16_t);
     struct { void** p; size_t n; } allocs[] = {
         { (void**)&c->grayL, B * c->gpitch * eye_h }, { (void**)&c->grayR, B * c->gpitch * eye_h },
-        { (void**)&c->pfL, B * npx * sizeof(uint2) }, { (void**)&c->pfR, B * npx * sizeof(uint2) },
+        { (void**)&c->rexp, B * eye_h * 4 * (size_t)c->rexp_wpw * sizeof(uint4) },
+        { (void**)&c->lexp, B * eye_h * (size_t)v3d_lexp_cols(eye_w) * 2 * sizeof(uint4) },
         { (void**)&c->C, vol }, { (void**)&c->S, vol },
         { (void**)&c->rec, B * (size_t)eye_h * c->W1 * sizeof(uint2) },
         { (void**)&c->raw, B * npx * 2 }, { (void**)&c->med, B * npx * 2 }, { (void**)&c->disp, B * npx * 2 },

@@ -24,7 +24,8 @@ struct v3d_ctx {
     // workspace (device)
     uint8_t *grayL, *grayR;      // [B][H][gpitch]
     size_t gpitch;
-    uint2 *pfL, *pfR;            // prefilter records [B][H][W]: {sobel v,lo,hi,0 | intensity v,lo,hi,0}
+    uint4 *rexp, *lexp;          // expanded BT operands (k_cost.cu): right [B][H][2][2][rexp_wpw], left [B][H][W+16][2]
+    int rexp_wpw;
     uint16_t *C, *S;             // [B][H][W1][D]
     uint2* rec;                  // WTA records [B][H][W1]
     int16_t *raw, *med, *disp;   // [B][H][W]
@@ -72,6 +73,8 @@ int v3d_launch_eyes_to_gray(v3d_ctx* ctx, const uint8_t* left_bgr, const uint8_t
 int v3d_launch_unsqueeze_bgr(const uint8_t* src, size_t pitch, size_t stride, int w, int h, int batch,
                              uint8_t* dst, size_t dpitch, size_t dstride, cudaStream_t st);
 // k_cost.cu
+int v3d_rexp_words(int W);
+int v3d_lexp_cols(int W);
 int v3d_launch_prefilter(v3d_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t gpitch,
                          size_t gstride, int batch, cudaStream_t st);
 int v3d_launch_cost(v3d_ctx* ctx, int batch, cudaStream_t st);
