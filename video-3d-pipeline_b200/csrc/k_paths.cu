@@ -14,6 +14,7 @@
 #include "path_common.cuh"
 
 #include <cooperative_groups.h>
+#include <type_traits>
 namespace cg = cooperative_groups;
 
 namespace {
@@ -276,73 +277,96 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     else if (rank < V3_CL - 1) right_x = cluster.map_shared_rank(xch, rank + 1) + (0 * 2 + 1) * 32 + lane;
     constexpr int PARSTRIDE = V3_NW * 2 * 32;
 
+    const int nv = min(max(W1 - gcol0, 0), CPW);      // columns of this warp inside the window
+    const bool has_right = gcol0 + CPW < W1;          // a column to the right of this warp's last one exists
     VT cq[CPW], sq[CPW];
     {
         const int y = sy > 0 ? 0 : H - 1;
+        const VT* Crow = C + ((size_t)y * W1 + gcol0) * 32;
+        const VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
 #pragma unroll
         for (int j = 0; j < CPW; j++)
-            if (gcol0 + j < W1) {
-                cq[j] = __ldg(C + ((size_t)y * W1 + gcol0 + j) * 32);
-                if (SMODE == S_ACCUM) sq[j] = S[((size_t)y * W1 + gcol0 + j) * 32];
+            if (j < nv) {
+                cq[j] = __ldg(Crow + j * 32);
+                if (SMODE == S_ACCUM) sq[j] = Srow[j * 32];
             }
     }
-    for (int i = 0; i < H; i++) {
+    VT* Md = Mst + (0 * COLS + lc0) * 32 + lane;      // this warp's state rows, one per direction
+    VT* Ml = Mst + (1 * COLS + lc0) * 32 + lane;
+    VT* Mr = Mst + (2 * COLS + lc0) * 32 + lane;
+    VT* xo = xch + (w * 2) * 32 + lane;
+    // FULL: all CPW columns are inside the window, so the unrolled column loop carries no predicate and the
+    // compiler can rename registers across columns instead of moving the carried state around.
+    auto row_body = [&](auto full_tag, int i) {
+        constexpr bool FULL = decltype(full_tag)::value;
         const int y = sy > 0 ? i : H - 1 - i;
         const int yn = sy > 0 ? i + 1 : H - 2 - i;
         const int par = i & 1;
-        xch[par * PARSTRIDE + (w * 2 + 0) * 32 + lane] = Mst[(1 * COLS + lc0 + CPW - 1) * 32 + lane];
-        xch[par * PARSTRIDE + (w * 2 + 1) * 32 + lane] = Mst[(2 * COLS + lc0) * 32 + lane];
+        xo[par * PARSTRIDE] = Ml[(CPW - 1) * 32];
+        xo[par * PARSTRIDE + 32] = Mr[0];
         cluster.sync();
         uint32_t carry[NR];
-        if (gcol0 > 0 && gcol0 < W1) unpack<NR>(left_x[par * PARSTRIDE], carry);
+        if (gcol0 > 0 && nv > 0) unpack<NR>(left_x[par * PARSTRIDE], carry);
         else {
 #pragma unroll
             for (int r = 0; r < NR; r++) carry[r] = 0;
         }
+        const bool more = i + 1 < H;
+        const VT* Cnext = C + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
+        VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
+        const VT* Snext = S + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
 #pragma unroll
         for (int j = 0; j < CPW; j++) {
-            if (gcol0 + j >= W1) break;
-            uint32_t Cr[NR], Sr[NR], L[NR], M[NR];
-            unpack<NR>(cq[j], Cr);
-            if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
-            if (i + 1 < H) {
-                cq[j] = __ldg(C + ((size_t)yn * W1 + gcol0 + j) * 32);
-                if (SMODE == S_ACCUM) sq[j] = S[((size_t)yn * W1 + gcol0 + j) * 32];
-            }
-            // (x, y-sy)
-            unpack<NR>(Mst[(0 * COLS + lc0 + j) * 32 + lane], M);
-            path_step<NR>(M, Cr, L, P1p, P2p, lane);
-            Mst[(0 * COLS + lc0 + j) * 32 + lane] = pack<NR>(M);
-#pragma unroll
-            for (int r = 0; r < NR; r++) Sr[r] = (SMODE == S_ACCUM) ? Sr[r] + L[r] : L[r];
-            // (x-1, y-sy): state arrives from the left neighbour column
-            {
-                uint32_t old[NR];
-                unpack<NR>(Mst[(1 * COLS + lc0 + j) * 32 + lane], old);
-#pragma unroll
-                for (int r = 0; r < NR; r++) M[r] = carry[r];
-                path_step<NR>(M, Cr, L, P1p, P2p, lane);
-                Mst[(1 * COLS + lc0 + j) * 32 + lane] = pack<NR>(M);
-#pragma unroll
-                for (int r = 0; r < NR; r++) { Sr[r] += L[r]; carry[r] = old[r]; }
-            }
-            // (x+1, y-sy): state arrives from the right neighbour column (still the old row's: ascending j)
-            {
-                if (gcol0 + j + 1 >= W1) {
-#pragma unroll
-                    for (int r = 0; r < NR; r++) M[r] = 0;
-                } else if (j + 1 < CPW) {
-                    unpack<NR>(Mst[(2 * COLS + lc0 + j + 1) * 32 + lane], M);
-                } else {
-                    unpack<NR>(right_x[par * PARSTRIDE], M);
+            if (FULL || j < nv) {
+                uint32_t Cr[NR], Sr[NR], L[NR], M[NR];
+                unpack<NR>(cq[j], Cr);
+                if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
+                if (more) {
+                    cq[j] = __ldg(Cnext + j * 32);
+                    if (SMODE == S_ACCUM) sq[j] = Snext[j * 32];
                 }
+                // (x, y-sy)
+                unpack<NR>(Md[j * 32], M);
                 path_step<NR>(M, Cr, L, P1p, P2p, lane);
-                Mst[(2 * COLS + lc0 + j) * 32 + lane] = pack<NR>(M);
+                Md[j * 32] = pack<NR>(M);
 #pragma unroll
-                for (int r = 0; r < NR; r++) Sr[r] += L[r];
+                for (int r = 0; r < NR; r++) Sr[r] = (SMODE == S_ACCUM) ? Sr[r] + L[r] : L[r];
+                // (x-1, y-sy): state arrives from the left neighbour column
+                {
+                    const VT oldv = Ml[j * 32];
+                    path_step<NR>(carry, Cr, L, P1p, P2p, lane);
+                    Ml[j * 32] = pack<NR>(carry);
+                    unpack<NR>(oldv, carry);
+#pragma unroll
+                    for (int r = 0; r < NR; r++) Sr[r] += L[r];
+                }
+                // (x+1, y-sy): state arrives from the right neighbour column (still the old row's: ascending j)
+                {
+                    if (j + 1 < CPW) {
+                        unpack<NR>(Mr[(j + 1) * 32], M);
+                        if (!FULL && j + 1 >= nv) {
+#pragma unroll
+                            for (int r = 0; r < NR; r++) M[r] = 0;
+                        }
+                    } else if (has_right) {
+                        unpack<NR>(right_x[par * PARSTRIDE], M);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < NR; r++) M[r] = 0;
+                    }
+                    path_step<NR>(M, Cr, L, P1p, P2p, lane);
+                    Mr[j * 32] = pack<NR>(M);
+#pragma unroll
+                    for (int r = 0; r < NR; r++) Sr[r] += L[r];
+                }
+                Srow[j * 32] = pack<NR>(Sr);
             }
-            S[((size_t)y * W1 + gcol0 + j) * 32] = pack<NR>(Sr);
         }
+    };
+    if (nv == CPW) {
+        for (int i = 0; i < H; i++) row_body(std::true_type{}, i);
+    } else {
+        for (int i = 0; i < H; i++) row_body(std::false_type{}, i);
     }
     cluster.sync();   // nobody may exit while a neighbour can still read its shared memory
 }

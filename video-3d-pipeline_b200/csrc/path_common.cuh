@@ -23,16 +23,17 @@ template <int NR>
 __device__ __forceinline__ void path_step(uint32_t (&M)[NR], const uint32_t (&C)[NR], uint32_t (&L)[NR],
                                           uint32_t P1p, uint32_t P2p, int lane)
 {
-    uint32_t up = __shfl_up_sync(V3D_FULL_MASK, M[NR - 1], 1);
-    uint32_t dn = __shfl_down_sync(V3D_FULL_MASK, M[0], 1);
-    // d = -1 and d = D do not exist: any value >= P2 is "infinity" because M <= P2 and P1 > 0
-    if (lane == 0) up = P2p;
-    if (lane == 31) dn = P2p;
+    const uint32_t up = __shfl_up_sync(V3D_FULL_MASK, M[NR - 1], 1);
+    const uint32_t dn = __shfl_down_sync(V3D_FULL_MASK, M[0], 1);
+    // d = -1 and d = D do not exist.  Substituting the cell's own value for the missing neighbour is
+    // exact (M[d] + P1 never beats M[d]), and costs nothing: only the byte-permute selector differs.
+    const uint32_t sel_up = lane == 0 ? 0x5454u : 0x5432u;
+    const uint32_t sel_dn = lane == 31 ? 0x3232u : 0x5432u;
     uint32_t sh[NR + 1];
-    sh[0] = __byte_perm(up, M[0], 0x5432);            // (M[d-1] for the even d, M[d-1] for the odd d)
+    sh[0] = __byte_perm(up, M[0], sel_up);            // (M[d-1] for the even d, M[d-1] for the odd d)
 #pragma unroll
     for (int k = 1; k < NR; k++) sh[k] = __byte_perm(M[k - 1], M[k], 0x5432);
-    sh[NR] = __byte_perm(M[NR - 1], dn, 0x5432);
+    sh[NR] = __byte_perm(M[NR - 1], dn, sel_dn);
     uint32_t m = 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < NR; k++) {
@@ -42,7 +43,7 @@ __device__ __forceinline__ void path_step(uint32_t (&M)[NR], const uint32_t (&C)
     }
     m = __vminu2(m, __byte_perm(m, 0, 0x1032));          // both halves = this lane's minimum
     const uint32_t mm = __reduce_min_sync(V3D_FULL_MASK, m);
-    const uint32_t neg = ((0x10000u - (mm & 0xffffu)) & 0xffffu) * 0x10001u;
+    const uint32_t neg = __vadd2(~mm, 0x00010001u);       // -min in both halves
 #pragma unroll
     for (int k = 0; k < NR; k++) M[k] = __viaddmin_s16x2(L[k], neg, P2p);
 }
