@@ -104,56 +104,14 @@ k_path_lr_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1
 //   .x = minS | best << 16      (best = 0xffff when the uniqueness test rejects the pixel)
 //   .y = S[best-1] | S[best+1] << 16
 // which k_select turns into the disparity (disp2 vote, sub-pixel, LR check).
+//
+// Per chunk of CH = 8 pixels the warp first walks the 8 path steps (lane = 2*NR consecutive
+// disparities, S_total written in place into the staged S chunk), then re-maps its lanes to
+// (pixel = lane / 4, quarter = lane % 4) so that all 8 pixels do their winner-takes-all at once:
+// each lane scans its quarter of one pixel's disparities from shared memory and the four quarters
+// meet through two shuffle-xor steps.  That replaces two warp-wide reductions per PIXEL by two
+// 4-lane reductions per CHUNK.
 // ------------------------------------------------------------------------------------------
-template <int NR, bool TAP_S>
-__device__ __forceinline__ void wta_step(uint32_t (&M)[NR], const typename Vec<NR>::T* cs, typename Vec<NR>::T* ss,
-                                         typename Vec<NR>::T* Stap, uint32_t P1p, uint32_t P2p, int uniq, int lane,
-                                         const uint32_t (&dc)[NR], const uint32_t (&idx)[NR], uint32_t* srow_w,
-                                         int i, int x, uint2& myrec)
-{
-    constexpr int D = 64 * NR;
-    uint32_t Cr[NR], Sr[NR], L[NR];
-    unpack<NR>(*cs, Cr);
-    unpack<NR>(*ss, Sr);
-    path_step<NR>(M, Cr, L, P1p, P2p, lane);
-#pragma unroll
-    for (int r = 0; r < NR; r++) Sr[r] += L[r];
-    if (TAP_S) Stap[(size_t)x * 32] = pack<NR>(Sr);
-    // first argmin through (S << 8 | d) keys
-    uint32_t key = 0xffffffffu;
-#pragma unroll
-    for (int r = 0; r < NR; r++) {
-        key = min(key, __byte_perm(Sr[r], dc[r], 0x7104));
-        key = min(key, __byte_perm(Sr[r], dc[r], 0x7325));
-    }
-    key = __reduce_min_sync(V3D_FULL_MASK, key);
-    const uint32_t best = key & 0xffu, minS = key >> 8;
-    // uniqueness: the smallest S over |d - best| > 1
-    const uint32_t off = ((1u - best) & 0xffffu) * 0x10001u;      // t = d - best + 1 in each half
-    uint32_t m2 = 0xffffffffu;
-#pragma unroll
-    for (int r = 0; r < NR; r++) {
-        const uint32_t t = __vadd2(idx[r], off);
-        const uint32_t e = __vadd2(__vminu2(t, 0x00030003u), 0xfffdfffdu);   // 0xfffd..0xffff iff t in {0,1,2}
-        m2 = __vminu2(m2, __vmaxu2(Sr[r], e));
-    }
-    m2 = __vminu2(m2, __byte_perm(m2, 0, 0x1032));
-    const uint32_t minS2 = __reduce_min_sync(V3D_FULL_MASK, m2) & 0xffffu;
-    const bool reject = minS2 * (uint32_t)(100 - uniq) < minS * 100u;
-    // neighbours of the minimum through a per-warp shared row (double buffered by step parity)
-    uint32_t* sr = srow_w + (i & 1) * (D / 2);
-#pragma unroll
-    for (int r = 0; r < NR; r++) sr[lane * NR + r] = Sr[r];
-    __syncwarp();
-    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sr);
-    const uint32_t sm1 = s16[best > 0 ? best - 1 : 0];
-    const uint32_t sp1 = s16[best < D - 1 ? best + 1 : D - 1];
-    if (lane == (i & 31)) {
-        myrec.x = (minS & 0xffffu) | ((reject ? 0xffffu : best) << 16);
-        myrec.y = sm1 | (sp1 << 16);
-    }
-}
-
 template <int NR, bool TAP_S>
 __global__ void __launch_bounds__(HW_WARPS * 32)
 k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, uint2* __restrict__ rec, int W1,
@@ -163,9 +121,10 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, ui
     constexpr int D = 64 * NR;
     constexpr int NST = 3;
     constexpr int STEP_B = 128 * NR;
+    constexpr int NU = 2 * NR;                   // uint4 (8 disparities each) per lane in the WTA phase
+    static_assert(CH == 8, "the WTA lane mapping assumes 8 pixels per chunk");
     extern __shared__ __align__(128) unsigned char hsm[];
     __shared__ __align__(8) uint64_t bars[HW_WARPS][NST];
-    __shared__ uint32_t srow[HW_WARPS][2][D / 2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int row = blockIdx.x * HW_WARPS + wib;
     if (row >= rows) return;
@@ -173,17 +132,16 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, ui
     unsigned char* sst = cst + NST * CH * STEP_B;
     const unsigned char* Cg = reinterpret_cast<const unsigned char*>(Cv) + (size_t)row * W1 * STEP_B;
     const unsigned char* Sg = reinterpret_cast<const unsigned char*>(Sv) + (size_t)row * W1 * STEP_B;
-    VT* Stap = reinterpret_cast<VT*>(Sv) + (size_t)row * W1 * 32 + lane;
+    uint4* Stap = reinterpret_cast<uint4*>(Sv) + (size_t)row * W1 * (STEP_B / 16);
     rec += (size_t)row * W1;
     const int nchunks = (W1 + CH - 1) / CH;
 
-    uint32_t dc[NR], idx[NR];
-#pragma unroll
-    for (int r = 0; r < NR; r++) {
-        const uint32_t d0 = 2 * NR * lane + 2 * r;
-        dc[r] = d0 | ((d0 + 1) << 8);
-        idx[r] = d0 | ((d0 + 1) << 16);
-    }
+    // WTA-phase identity of this lane
+    const int wp = lane >> 2, wq = lane & 3;
+    // visit the NU uint4 in a lane-dependent rotation so that a quarter-warp's 128-bit loads hit 8 different
+    // 16-byte bank groups (the natural order is a 4-way conflict for D = 128)
+    const int rot = NR == 2 ? (((wq >> 1) + 2 * (wp & 1)) & 3) : 0;
+
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < NST; s++) mbar_init(&bars[wib][s], 1);
@@ -207,35 +165,88 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, ui
     uint32_t M[NR];
 #pragma unroll
     for (int r = 0; r < NR; r++) M[r] = 0;
-    uint2 myrec = make_uint2(0, 0);
-    int i = 0;                                   // step counter, x = W1 - 1 - i
     for (int c = 0; c < nchunks; c++) {
         const int st = c % NST;
         mbar_wait(&bars[wib][st], (uint32_t)((c / NST) & 1));
         const int hi = W1 - c * CH, lo = max(hi - CH, 0), n = hi - lo;
         const VT* cs = reinterpret_cast<const VT*>(cst + st * CH * STEP_B) + lane;
         VT* ss = reinterpret_cast<VT*>(sst + st * CH * STEP_B) + lane;
+        // ---- phase 1: the path steps, right to left; S_total replaces S in the stage ----
         if (n == CH) {
 #pragma unroll
-            for (int j = CH - 1; j >= 0; j--, i++) {
-                wta_step<NR, TAP_S>(M, cs + j * 32, ss + j * 32, Stap, P1p, P2p, uniq, lane, dc, idx, &srow[wib][0][0],
-                                    i, lo + j, myrec);
-                if ((i & 31) == 31) rec[W1 - 1 - i + (31 - lane)] = myrec;     // 32 records, coalesced
+            for (int j = CH - 1; j >= 0; j--) {
+                uint32_t Cr[NR], Sr[NR], L[NR];
+                unpack<NR>(cs[j * 32], Cr);
+                unpack<NR>(ss[j * 32], Sr);
+                path_step<NR>(M, Cr, L, P1p, P2p, lane);
+#pragma unroll
+                for (int r = 0; r < NR; r++) Sr[r] += L[r];
+                ss[j * 32] = pack<NR>(Sr);
             }
         } else {
-            for (int j = n - 1; j >= 0; j--, i++) {
-                wta_step<NR, TAP_S>(M, cs + j * 32, ss + j * 32, Stap, P1p, P2p, uniq, lane, dc, idx, &srow[wib][0][0],
-                                    i, lo + j, myrec);
-                if ((i & 31) == 31) rec[W1 - 1 - i + (31 - lane)] = myrec;
+            for (int j = n - 1; j >= 0; j--) {
+                uint32_t Cr[NR], Sr[NR], L[NR];
+                unpack<NR>(cs[j * 32], Cr);
+                unpack<NR>(ss[j * 32], Sr);
+                path_step<NR>(M, Cr, L, P1p, P2p, lane);
+#pragma unroll
+                for (int r = 0; r < NR; r++) Sr[r] += L[r];
+                ss[j * 32] = pack<NR>(Sr);
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: winner-takes-all of the chunk's pixels, 4 lanes per pixel ----
+        {
+            const uint4* px = reinterpret_cast<const uint4*>(sst + st * CH * STEP_B) + wp * (STEP_B / 16) + wq * NU;
+            uint4 v[NU];
+            uint32_t key = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < NU; k++) {
+                const int u = NR == 2 ? ((k + rot) & 3) : k;
+                v[k] = px[u];
+                const uint32_t d0 = (uint32_t)(wq * NU + u) * 8;
+                const uint32_t dc0 = d0 | ((d0 + 1) << 8);
+                const uint32_t w[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t dc = dc0 + t * 0x0202u;
+                    key = __vimin3_u32(key, __byte_perm(w[t], dc, 0x7104), __byte_perm(w[t], dc, 0x7325));
+                }
+                if (TAP_S && wp < n) Stap[(size_t)(lo + wp) * (STEP_B / 16) + wq * NU + u] = v[k];
+            }
+            key = min(key, __shfl_xor_sync(V3D_FULL_MASK, key, 1));
+            key = min(key, __shfl_xor_sync(V3D_FULL_MASK, key, 2));
+            const uint32_t best = key & 0xffu, minS = key >> 8;
+            // uniqueness: the smallest S over |d - best| > 1
+            const uint32_t off = ((1u - best) & 0xffffu) * 0x10001u;      // t = d - best + 1 in each half
+            uint32_t m2 = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < NU; k++) {
+                const int u = NR == 2 ? ((k + rot) & 3) : k;
+                const uint32_t d0 = (uint32_t)(wq * NU + u) * 8;
+                const uint32_t idx0 = d0 | ((d0 + 1) << 16);
+                const uint32_t w[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t tt = __vadd2(idx0 + t * 0x00020002u, off);
+                    const uint32_t e = __vadd2(__vminu2(tt, 0x00030003u), 0xfffdfffdu);   // 0xfffd.. iff tt in {0,1,2}
+                    m2 = __vminu2(m2, __vmaxu2(w[t], e));
+                }
+            }
+            m2 = __vminu2(m2, __byte_perm(m2, 0, 0x1032));
+            m2 = __vminu2(m2, __shfl_xor_sync(V3D_FULL_MASK, m2, 1));
+            m2 = __vminu2(m2, __shfl_xor_sync(V3D_FULL_MASK, m2, 2));
+            const uint32_t minS2 = m2 & 0xffffu;
+            if (wq == 0 && wp < n) {
+                const bool reject = minS2 * (uint32_t)(100 - uniq) < minS * 100u;
+                const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sst + st * CH * STEP_B + wp * STEP_B);
+                const uint32_t sm1 = s16[best > 0 ? best - 1 : 0];
+                const uint32_t sp1 = s16[best < D - 1 ? best + 1 : D - 1];
+                rec[lo + wp] = make_uint2((minS & 0xffffu) | ((reject ? 0xffffu : best) << 16), sm1 | (sp1 << 16));
             }
         }
         __syncwarp();                            // every lane is done reading this stage
         if (lane == 0 && c + NST < nchunks) issue(c + NST);
-    }
-    // flush the last partial group of records: steps i0 .. i-1 live in lanes 0 .. (i-1-i0)
-    if (i & 31) {
-        const int i0 = i & ~31;
-        if (i0 + lane < i) rec[W1 - 1 - (i0 + lane)] = myrec;
     }
 }
 
