@@ -111,6 +111,7 @@ k_guided_coeff(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* 
     }
     __syncthreads();
     const float4 cc = centre;
+#pragma unroll 3
     for (int i = tid; i < RW * RH; i += 256) {
         const int j = i / RW, t = i - j * RW;
         uint32_t rgb;
@@ -218,10 +219,30 @@ k_guided_apply(const float4* __restrict__ ab, const uint8_t* __restrict__ guide,
     out += (size_t)b * gw * gh;
     if (qout) qout += (size_t)b * gw * gh;
 
-    for (int i = tid; i < RW * RH; i += 256) {
-        const int j = i / RW, t = i - j * RW;
-        const int X = reflect_idx(X0 - r + t, gw), Y = reflect_idx(Y0 - r + j, gh);
-        base[j * BP + t] = __ldg(ab + (size_t)Y * gw + X);
+    if (RT > 0) {
+        // all of this thread's region loads are issued before the first one is stored
+        constexpr int RWc = GT + 2 * (RT > 0 ? RT : 1);
+        constexpr int NL = (RWc * RWc + 255) / 256;
+        float4 tmp[NL];
+#pragma unroll
+        for (int k = 0; k < NL; k++) {
+            const int i = tid + k * 256;
+            if (i < RWc * RWc) {
+                const int j = i / RWc, t = i - j * RWc;
+                tmp[k] = __ldg(ab + (size_t)reflect_idx(Y0 - r + j, gh) * gw + reflect_idx(X0 - r + t, gw));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NL; k++) {
+            const int i = tid + k * 256;
+            if (i < RWc * RWc) base[(i / RWc) * BP + (i % RWc)] = tmp[k];
+        }
+    } else {
+        for (int i = tid; i < RW * RH; i += 256) {
+            const int j = i / RW, t = i - j * RW;
+            const int X = reflect_idx(X0 - r + t, gw), Y = reflect_idx(Y0 - r + j, gh);
+            base[j * BP + t] = __ldg(ab + (size_t)Y * gw + X);
+        }
     }
     __syncthreads();
     for (int it = tid; it < RH * (GT / GRUN); it += 256) {
