@@ -295,79 +295,106 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     VT* Ml = Mst + (1 * COLS + lc0) * 32 + lane;
     VT* Mr = Mst + (2 * COLS + lc0) * 32 + lane;
     VT* xo = xch + (w * 2) * 32 + lane;
-    // FULL: all CPW columns are inside the window, so the unrolled column loop carries no predicate and the
-    // compiler can rename registers across columns instead of moving the carried state around.
-    auto row_body = [&](auto full_tag, int i) {
-        constexpr bool FULL = decltype(full_tag)::value;
+    // One column: the three path steps, the state write-back and the S store.  inl / inr are the previous
+    // row's states arriving from the left / right neighbour column.
+    auto do_col = [&](int j, const uint32_t (&inl)[NR], const uint32_t (&inr)[NR], bool more, const VT* Cnext,
+                      const VT* Snext, VT* Srow) {
+        uint32_t Cr[NR], Sr[NR], L[NR], M[NR];
+        unpack<NR>(cq[j], Cr);
+        if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
+        if (more) {
+            cq[j] = __ldg(Cnext + j * 32);
+            if (SMODE == S_ACCUM) sq[j] = Snext[j * 32];
+        }
+        unpack<NR>(Md[j * 32], M);                               // (x, y-sy)
+        path_step<NR>(M, Cr, L, P1p, P2p, lane);
+        Md[j * 32] = pack<NR>(M);
+#pragma unroll
+        for (int r = 0; r < NR; r++) { Sr[r] = (SMODE == S_ACCUM) ? Sr[r] + L[r] : L[r]; M[r] = inl[r]; }
+        path_step<NR>(M, Cr, L, P1p, P2p, lane);                 // (x-1, y-sy)
+        Ml[j * 32] = pack<NR>(M);
+#pragma unroll
+        for (int r = 0; r < NR; r++) { Sr[r] += L[r]; M[r] = inr[r]; }
+        path_step<NR>(M, Cr, L, P1p, P2p, lane);                 // (x+1, y-sy)
+        Mr[j * 32] = pack<NR>(M);
+#pragma unroll
+        for (int r = 0; r < NR; r++) Sr[r] += L[r];
+        Srow[j * 32] = pack<NR>(Sr);
+    };
+    const uint32_t zeros[NR] = {};
+    for (int i = 0; i < H; i++) {
         const int y = sy > 0 ? i : H - 1 - i;
         const int yn = sy > 0 ? i + 1 : H - 2 - i;
         const int par = i & 1;
-        xo[par * PARSTRIDE] = Ml[(CPW - 1) * 32];
-        xo[par * PARSTRIDE + 32] = Mr[0];
-        cluster.sync();
-        uint32_t carry[NR];
-        if (gcol0 > 0 && nv > 0) unpack<NR>(left_x[par * PARSTRIDE], carry);
-        else {
-#pragma unroll
-            for (int r = 0; r < NR; r++) carry[r] = 0;
-        }
         const bool more = i + 1 < H;
         const VT* Cnext = C + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
         VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
         const VT* Snext = S + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
+        xo[par * PARSTRIDE] = Ml[(CPW - 1) * 32];
+        xo[par * PARSTRIDE + 32] = Mr[0];
+        cluster.barrier_arrive();
+        if (nv == CPW && CPW >= 3) {
+            // Full warp: the interior columns need nothing from other warps, so they run between the
+            // barrier's arrive and wait; only the two edge columns wait for the neighbours' states.
+            uint32_t carry[NR], save_r1[NR], inr[NR];
+            unpack<NR>(Ml[0], carry);                            // old state of column 0 -> column 1
+            unpack<NR>(Mr[1 * 32], save_r1);                     // old state of column 1 -> column 0 (used last)
 #pragma unroll
-        for (int j = 0; j < CPW; j++) {
-            if (FULL || j < nv) {
-                uint32_t Cr[NR], Sr[NR], L[NR], M[NR];
-                unpack<NR>(cq[j], Cr);
-                if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
-                if (more) {
-                    cq[j] = __ldg(Cnext + j * 32);
-                    if (SMODE == S_ACCUM) sq[j] = Snext[j * 32];
-                }
-                // (x, y-sy)
-                unpack<NR>(Md[j * 32], M);
-                path_step<NR>(M, Cr, L, P1p, P2p, lane);
-                Md[j * 32] = pack<NR>(M);
+            for (int j = 1; j < CPW - 1; j++) {
+                uint32_t nextcarry[NR];
+                unpack<NR>(Ml[j * 32], nextcarry);
+                unpack<NR>(Mr[(j + 1) * 32], inr);
+                do_col(j, carry, inr, more, Cnext, Snext, Srow);
 #pragma unroll
-                for (int r = 0; r < NR; r++) Sr[r] = (SMODE == S_ACCUM) ? Sr[r] + L[r] : L[r];
-                // (x-1, y-sy): state arrives from the left neighbour column
-                {
-                    const VT oldv = Ml[j * 32];
-                    path_step<NR>(carry, Cr, L, P1p, P2p, lane);
-                    Ml[j * 32] = pack<NR>(carry);
-                    unpack<NR>(oldv, carry);
+                for (int r = 0; r < NR; r++) carry[r] = nextcarry[r];
+            }
+            cluster.barrier_wait();
+            uint32_t edge[NR];
+            if (gcol0 > 0) unpack<NR>(left_x[par * PARSTRIDE], edge);
+            else {
 #pragma unroll
-                    for (int r = 0; r < NR; r++) Sr[r] += L[r];
-                }
-                // (x+1, y-sy): state arrives from the right neighbour column (still the old row's: ascending j)
-                {
+                for (int r = 0; r < NR; r++) edge[r] = 0;
+            }
+            do_col(0, edge, save_r1, more, Cnext, Snext, Srow);
+            if (has_right) unpack<NR>(right_x[par * PARSTRIDE], edge);
+            else {
+#pragma unroll
+                for (int r = 0; r < NR; r++) edge[r] = 0;
+            }
+            do_col(CPW - 1, carry, edge, more, Cnext, Snext, Srow);
+        } else {
+            cluster.barrier_wait();
+            uint32_t carry[NR], inr[NR];
+            if (gcol0 > 0 && nv > 0) unpack<NR>(left_x[par * PARSTRIDE], carry);
+            else {
+#pragma unroll
+                for (int r = 0; r < NR; r++) carry[r] = 0;
+            }
+#pragma unroll
+            for (int j = 0; j < CPW; j++) {
+                if (j < nv) {
+                    uint32_t nextcarry[NR];
+                    unpack<NR>(Ml[j * 32], nextcarry);
                     if (j + 1 < CPW) {
-                        unpack<NR>(Mr[(j + 1) * 32], M);
-                        if (!FULL && j + 1 >= nv) {
+                        unpack<NR>(Mr[(j + 1) * 32], inr);
+                        if (j + 1 >= nv) {
 #pragma unroll
-                            for (int r = 0; r < NR; r++) M[r] = 0;
+                            for (int r = 0; r < NR; r++) inr[r] = 0;
                         }
                     } else if (has_right) {
-                        unpack<NR>(right_x[par * PARSTRIDE], M);
+                        unpack<NR>(right_x[par * PARSTRIDE], inr);
                     } else {
 #pragma unroll
-                        for (int r = 0; r < NR; r++) M[r] = 0;
+                        for (int r = 0; r < NR; r++) inr[r] = 0;
                     }
-                    path_step<NR>(M, Cr, L, P1p, P2p, lane);
-                    Mr[j * 32] = pack<NR>(M);
+                    do_col(j, carry, inr, more, Cnext, Snext, Srow);
 #pragma unroll
-                    for (int r = 0; r < NR; r++) Sr[r] += L[r];
+                    for (int r = 0; r < NR; r++) carry[r] = nextcarry[r];
                 }
-                Srow[j * 32] = pack<NR>(Sr);
             }
         }
-    };
-    if (nv == CPW) {
-        for (int i = 0; i < H; i++) row_body(std::true_type{}, i);
-    } else {
-        for (int i = 0; i < H; i++) row_body(std::false_type{}, i);
     }
+    (void)zeros;
     cluster.sync();   // nobody may exit while a neighbour can still read its shared memory
 }
 
