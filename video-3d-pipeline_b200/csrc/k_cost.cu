@@ -102,37 +102,56 @@ k_prefilter_expand(const uint8_t* __restrict__ left, const uint8_t* __restrict__
 //   vertical (2R+1)-row sum: sliding window in registers (ring of 2R+1 packed pix values)
 //   horizontal (2R+1)-column sum: through shared memory, clamped in WINDOW coordinates
 // ---------------------------------------------------------------------------------------------
-constexpr int CNST = 3;       // staged rows in flight
-
-template <int NR>
+// The row loop is unrolled by U = max(K, 3) rows and the kernel keeps U staged rows and U vertical-sum
+// buffers, so that the ring slot (ph % K), the staging buffer and the vbuf slot of a row are all
+// compile-time constants inside the unrolled body: no stage/parity bookkeeping instructions.
+template <int NR, int R>
 struct CostSmem {
     static constexpr int D = 64 * NR;
+    static constexpr int K = 2 * R + 1;
+    static constexpr int U = K >= 3 ? K : 3;
     static constexpr int NWORDS = D / 2 + 10;
-    uint4 rbuf[CNST][2][2][NWORDS];   // [stage][channel][copy][word] = {v, -v, lo, -hi} pairs of the right image
-    uint4 lbuf[CNST][TXW][2];         // [stage][column][channel]     = {u, -u, lo, -hi} of the left image
-    uint32_t vbuf[2][TXW][D / 2];     // [row parity][column][pair]   = vertical sums
-    uint64_t bar[CNST];
+    uint4 rbuf[U][2][2][NWORDS];      // [stage][channel][copy][word] = {v, -v, lo, -hi} pairs of the right image
+    uint4 lbuf[U][TXW][2];            // [stage][column][channel]     = {u, -u, lo, -hi} of the left image
+    uint32_t vbuf[U][TXW][D / 2];     // [slot][column][pair]         = vertical sums
+    uint64_t bar[U];
 };
+
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar_addr), "r"(parity) : "memory");
+}
 
 template <int NR, int R>
 __global__ void __launch_bounds__(TXW * 32)
 k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, uint32_t* __restrict__ C,
        int W, int H, int W1, int band_h)
 {
+    using SM = CostSmem<NR, R>;
     constexpr int D = 64 * NR;
-    constexpr int K = 2 * R + 1;
+    constexpr int K = SM::K, U = SM::U;
     constexpr int TX = TXW - 2 * R;
-    constexpr int NWORDS = CostSmem<NR>::NWORDS;
-    __shared__ __align__(128) CostSmem<NR> sm;
+    constexpr int NWORDS = SM::NWORDS;
+    extern __shared__ __align__(128) unsigned char cost_smem[];
+    SM& sm = *reinterpret_cast<SM*>(cost_smem);
 
     const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;
     const int b = blockIdx.z;
     const int xs = blockIdx.x * TX;
     const int x = xs - R + c;                       // window column of this warp
-    const bool valid_col = (x >= 0 && x < W1);
     const bool inner = (c >= R && c < TXW - R && x < W1);
     const int y0 = blockIdx.y * band_h, y1 = min(H, y0 + band_h);
-    const int ystart = y0 - R, yend = y1 + R;
+    const int ystart = y0 - R;
+    const int nrows = (y1 + R - ystart + U - 1) / U * U;    // padded to whole unrolled groups
+    const int yend = ystart + nrows;
 
     // reversed element index of the strip's right-most image column, and the first staged word of each copy
     const int Xhi = xs - R + (TXW - 1) + D;
@@ -146,12 +165,11 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < CNST; s++) mbar_init(&sm.bar[s], 1);
+        for (int s = 0; s < U; s++) mbar_init(&sm.bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int r) {                       // thread 0 only: stage image row clamp(r) for sweep row r
-        const int st = (r - ystart) % CNST;
+    auto issue = [&](int r, int st) {               // thread 0 only: stage image row clamp(r) into stage st
         const int rr = min(max(r, 0), H - 1);
         const uint4* rrow = rexp + ((size_t)(b * H + rr) * 4) * wpw;
         constexpr uint32_t RB = NWORDS * 16, LB = TXW * 2 * 16;
@@ -163,8 +181,8 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
         bulk_g2s(&sm.lbuf[st][0][0], lexp + ((size_t)(b * H + rr) * (W + TXW) + Xl0) * 2, LB, &sm.bar[st]);
     };
     if (tid == 0) {
-        issue(ystart);
-        if (ystart + 1 < yend) issue(ystart + 1);
+#pragma unroll
+        for (int s = 0; s < U - 1; s++) issue(ystart + s, s);     // U-1 rows in flight
     }
 
     uint32_t ring[K][NR];
@@ -175,30 +193,35 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
 #pragma unroll
         for (int i = 0; i < K; i++) ring[i][k] = 0;
     }
-    int nb_off[K];                                  // neighbour columns, clamped in WINDOW coordinates
+    // per-thread shared-memory addresses (32-bit) and the clamped neighbour columns of the horizontal sum
+    const uint32_t bar0 = smem_u32(&sm.bar[0]);
+    const uint4* rs_p = &sm.rbuf[0][0][copy][wrel + lane];
+    const uint4* ri_p = &sm.rbuf[0][1][copy][wrel + lane];
+    constexpr int RSTG = 2 * 2 * NWORDS;            // uint4 per stage
+    const uint4* l_p = &sm.lbuf[0][c][0];
+    constexpr int LSTG = TXW * 2;
+    uint32_t* v_p = &sm.vbuf[0][c][lane];
+    constexpr int VSTG = TXW * (D / 2);
+    const uint32_t* vb = &sm.vbuf[0][0][lane];
+    int nb_off[K];
 #pragma unroll
-    for (int dx = -R; dx <= R; dx++) nb_off[dx + R] = (min(max(x + dx, 0), W1 - 1) - (xs - R)) * (D / 2) + lane;
-    uint32_t* out_col = C + (((size_t)b * H) * W1 + x) * (D / 2) + lane;
+    for (int dx = -R; dx <= R; dx++) nb_off[dx + R] = (min(max(x + dx, 0), W1 - 1) - (xs - R)) * (D / 2);
+    uint32_t* out = C + (((ptrdiff_t)b * H + (ystart - R)) * W1 + x) * (D / 2) + lane;   // output row of sweep row ystart
     const size_t out_row = (size_t)W1 * (D / 2);
 
-    int st = 0, cur = 0;
-    uint32_t phase = 0;
-    for (int row = ystart; row < yend; row += K) {
+    uint32_t parity = 0;
+    for (int row = ystart; row < yend; row += U, parity ^= 1) {
 #pragma unroll
-        for (int ph = 0; ph < K; ph++) {
+        for (int ph = 0; ph < U; ph++) {
             const int r = row + ph;
-            if (r >= yend) break;
-            mbar_wait(&sm.bar[st], phase);
-            if (valid_col) {
-                const uint4 ls = sm.lbuf[st][c][0];
-                const uint4 li = sm.lbuf[st][c][1];
-                const uint4* rs_p = &sm.rbuf[st][0][copy][wrel + lane];
-                const uint4* ri_p = &sm.rbuf[st][1][copy][wrel + lane];
-                uint32_t* v_p = &sm.vbuf[cur][c][lane];
+            mbar_wait_a(bar0 + ph * 8, parity);
+            {
+                const uint4 ls = l_p[ph * LSTG + 0];
+                const uint4 li = l_p[ph * LSTG + 1];
 #pragma unroll
                 for (int k = 0; k < NR; k++) {
-                    const uint4 rs = rs_p[32 * k];
-                    const uint4 ri = ri_p[32 * k];
+                    const uint4 rs = rs_p[ph * RSTG + 32 * k];
+                    const uint4 ri = ri_p[ph * RSTG + 32 * k];
                     // {x: v, y: -v, z: lo, w: -hi}
                     uint32_t c0 = __vimax_s16x2_relu(__vadd2(ls.x, rs.w), __vadd2(rs.z, ls.y));
                     uint32_t c1 = __vimax_s16x2_relu(__vadd2(rs.x, ls.w), __vadd2(ls.z, rs.y));
@@ -207,54 +230,57 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
                     c1 = __vimax_s16x2_relu(__vadd2(ri.x, li.w), __vadd2(li.z, ri.y));
                     const uint32_t bi = __vminu2(c0, c1);
                     const uint32_t pix = bs + ((bi >> 2) & 0x3fff3fffu);
-                    V[k] = V[k] + pix - ring[ph][k];     // halves never borrow: V includes ring[ph]
-                    ring[ph][k] = pix;
-                    v_p[32 * k] = V[k];
+                    V[k] = V[k] + pix - ring[ph % K][k];     // halves never borrow: V includes the ring slot
+                    ring[ph % K][k] = pix;
+                    v_p[ph * VSTG + 32 * k] = V[k];
                 }
             }
-            __syncthreads();        // vbuf[cur] complete; every thread is done with the previous row's stage
-            if (tid == 0 && r + 2 < yend) issue(r + 2);     // refills the stage the previous row used
+            __syncthreads();        // vbuf[ph] complete; every thread is done with the previous row's stage
+            if (tid == 0 && r + U - 1 < yend) issue(r + U - 1, (ph + U - 1) % U);    // refills the previous row's stage
             const int yo = r - R;
-            if (inner && yo >= y0) {
-                const uint32_t* vb = &sm.vbuf[cur][0][0];
-                uint32_t* out = out_col + (size_t)yo * out_row;
+            if (inner && yo >= y0 && yo < y1) {
 #pragma unroll
                 for (int k = 0; k < NR; k++) {
                     uint32_t acc = 0;
 #pragma unroll
-                    for (int dx = 0; dx < K; dx++) acc += vb[nb_off[dx] + 32 * k];
+                    for (int dx = 0; dx < K; dx++) acc += vb[ph * VSTG + nb_off[dx] + 32 * k];
                     out[32 * k] = acc;
                 }
             }
-            cur ^= 1;
-            if (++st == CNST) { st = 0; phase ^= 1; }
+            out += out_row;
         }
     }
+}
+
+template <int NR, int R>
+int launch_cost_nr(v3d_ctx* ctx, int batch, cudaStream_t st)
+{
+    constexpr int K = 2 * R + 1, U = K >= 3 ? K : 3;
+    const int band_h = U * 26 - 2 * R;           // band_h + 2R is a whole number of unrolled groups
+    const size_t smem = sizeof(CostSmem<NR, R>) + 128;
+    const int key = NR * 8 + R;
+    if (!(ctx->cost_attr_set & (1ull << key))) {
+        V3D_CUDA(cudaFuncSetAttribute(k_cost<NR, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->cost_attr_set |= (1ull << key);
+    }
+    const int W1 = ctx->W1, H = ctx->H;
+    dim3 grid((W1 + (TXW - 2 * R) - 1) / (TXW - 2 * R), (H + band_h - 1) / band_h, batch), block(TXW * 32);
+    k_cost<NR, R><<<grid, block, smem, st>>>(ctx->rexp, ctx->rexp_wpw, ctx->lexp, reinterpret_cast<uint32_t*>(ctx->C),
+                                             ctx->W, H, W1, band_h);
+    V3D_LAUNCHED(ctx, 1);
+    return V3D_OK;
 }
 
 template <int NR>
 int launch_cost_r(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
-    const int band_h = 128;
-    uint32_t* C = reinterpret_cast<uint32_t*>(ctx->C);
-    const int W = ctx->W, H = ctx->H, W1 = ctx->W1;
-    dim3 block(TXW * 32);
-#define V3D_COST_CASE(RR)                                                                              \
-    case RR: {                                                                                         \
-        dim3 grid((W1 + (TXW - 2 * RR) - 1) / (TXW - 2 * RR), (H + band_h - 1) / band_h, batch);        \
-        k_cost<NR, RR><<<grid, block, 0, st>>>(ctx->rexp, ctx->rexp_wpw, ctx->lexp, C, W, H, W1, band_h); \
-        break;                                                                                         \
-    }
     switch (ctx->R) {
-        V3D_COST_CASE(0)
-        V3D_COST_CASE(1)
-        V3D_COST_CASE(2)
-        V3D_COST_CASE(3)
-        default: return v3d_fail(V3D_EINVAL, "blockSize %d unsupported", ctx->p.blockSize);
+        case 0: return launch_cost_nr<NR, 0>(ctx, batch, st);
+        case 1: return launch_cost_nr<NR, 1>(ctx, batch, st);
+        case 2: return launch_cost_nr<NR, 2>(ctx, batch, st);
+        case 3: return launch_cost_nr<NR, 3>(ctx, batch, st);
     }
-#undef V3D_COST_CASE
-    V3D_LAUNCHED(ctx, 1);
-    return V3D_OK;
+    return v3d_fail(V3D_EINVAL, "blockSize %d unsupported", ctx->p.blockSize);
 }
 
 }  // namespace
