@@ -385,8 +385,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=30, help="frames per step per GPU")
-    ap.add_argument("--lanes", type=int, default=2, help="streams/contexts the batch is split over")
+    ap.add_argument("--batch", type=int, default=45, help="frames per step per GPU")
+    ap.add_argument("--lanes", type=int, default=3, help="streams/contexts the batch is split over")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

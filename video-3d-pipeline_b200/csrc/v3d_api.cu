@@ -167,6 +167,7 @@ int v3d_destroy(v3d_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     drain_spans(ctx);
+    if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_done); }
     free_all(ctx);
     delete ctx;
     return V3D_OK;
@@ -382,17 +383,28 @@ int v3d_depth_frames_host(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, 
         V3dScope scope(ctx, ST_COPY, st);
         V3D_CUDA(cudaMemcpyAsync(ctx->in_dev, sbs_bgr_host, frame * batch, cudaMemcpyHostToDevice, st));
         if (guide_rgb_host) {
+            // the guide (2/3 of the input bytes) is not needed before the upscale: upload it on the
+            // context's copy stream so that it overlaps the whole SGBM chain
             const size_t gbytes = (size_t)gw * gh * 3 * batch;
             if ((rc = ensure(ctx, (void**)&ctx->guide_dev, &ctx->guide_bytes, gbytes))) return rc;
             if ((rc = ensure(ctx, (void**)&ctx->out_dev, &ctx->out_bytes, (size_t)gw * gh * 2 * batch))) return rc;
-            V3D_CUDA(cudaMemcpyAsync(ctx->guide_dev, guide_rgb_host, gbytes, cudaMemcpyHostToDevice, st));
+            if (!ctx->copy_stream) {
+                V3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+                V3D_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+            }
+            V3D_CUDA(cudaMemcpyAsync(ctx->guide_dev, guide_rgb_host, gbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            V3D_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
         }
     }
     rc = v3d_depth_frames(ctx, ctx->in_dev, (size_t)sbs_w * 3, frame, sbs_w, h, batch, unsqueeze, ctx->disp,
                           depth_f32_host ? ctx->f32_tmp : nullptr, depth_u16_host || guide_rgb_host ? ctx->u16_tmp : nullptr,
-                          guide_rgb_host ? ctx->guide_dev : nullptr, gw, gh, r, eps,
-                          guide_rgb_host ? ctx->out_dev : nullptr, stream);
+                          nullptr, 0, 0, r, eps, nullptr, stream);
     if (rc) return rc;
+    if (guide_rgb_host) {
+        V3D_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+        if ((rc = v3d_guided_upscale(ctx, ctx->u16_tmp, ctx->W, ctx->H, ctx->guide_dev, gw, gh, batch, r, eps,
+                                     ctx->out_dev, nullptr, stream))) return rc;
+    }
     {
         V3dScope scope(ctx, ST_COPY, st);
         if (disp_host) V3D_CUDA(cudaMemcpyAsync(disp_host, ctx->disp, npx * 2 * batch, cudaMemcpyDeviceToHost, st));

@@ -38,6 +38,7 @@ struct v3d_ctx {
     uint8_t* in_dev; size_t in_bytes;      // host-API staging: SBS frames
     uint8_t* guide_dev; size_t guide_bytes;
     uint16_t* out_dev; size_t out_bytes;
+    cudaStream_t copy_stream; cudaEvent_t copy_done;   // host entry point: guide upload overlaps the SGBM chain
     size_t bytes;
     int last_batch;
 
