@@ -48,6 +48,15 @@ ALG_BYTES_FUSED = SBS_BYTES + GUIDE_BYTES + OUT_BYTES    # 53 913 6
 W1 = EYE_W - D
 CELLS = W1 * EYE_H * D
 ALG_IOPS = (31 + 9 * 5) * CELLS                          # 18.8 Gop
+# DRAM bytes per frame measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum of a
+# 15-frame launch / 15), see profiles/README.md; keyed by bench stage.
+NCU_DRAM_BYTES_PER_FRAME = {
+    "cost": (0.488135e9 + 7.374558e9) / 15,
+    "vertical": (7.432115e9 + 7.387566e9) / 15,
+    "lr": (14.863591e9 + 7.389767e9) / 15,
+    "wta": (14.864166e9 + 0.235124e9) / 15,
+    "guided": (0.435929e9 + 1.934632e9 + 2.364077e9 + 0.246581e9) / 2 / 15,
+}
 
 
 def workload_config(batch, n_gpus, lanes=1):
@@ -323,24 +332,34 @@ def run_ours(args):
             peaks = json.loads(pk.read_text())
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        # dominant kernel family = the path-aggregation launches (4 of them for MODE_SGBM; the 5th is in 'wta')
-        n_path_kernels = 2      # fused vertical sweep + left-to-right pass (the right-to-left pass is 'wta')
-        dom_name = max(("cost", "paths", "wta", "guided"), key=lambda k: stages.get(k, 0.0))
-        dom_ms = stages[dom_name] / (n_path_kernels if dom_name == "paths" else (2 if dom_name == "guided" else 1))
+        # One stage timer = one kernel (guided = two).  The dominant kernel is the largest of them.
+        vol = 2.0 * CELLS                 # one uint16 cost volume, bytes per frame
+        kernels = {   # stage -> (kernel name, launches in the stage, design bytes per frame)
+            "cost": ("k_cost", 1, vol + 0.15e9),
+            "vertical": ("k_path_vert3", 1, 2 * vol),
+            "lr": ("k_path_lr_tma", 1, 3 * vol),
+            "wta": ("k_path_rl_wta_tma", 1, 2 * vol),
+            "guided": ("k_guided_coeff + k_guided_apply (avg of 2)", 2, (GUIDE_BYTES + 16 * GW * GH) / 2 + GW * GH * 9.0),
+        }
+        dom_name = max(kernels, key=lambda k: stages.get(k, 0.0) / kernels[k][1])
+        kname, nl, design_pf = kernels[dom_name]
+        dom_ms = stages[dom_name] / nl
         alg_bytes = (ALG_BYTES_FUSED if dom_name == "guided" else ALG_BYTES_DEPTH) * Bl
         achieved = alg_bytes / (dom_ms / 1000.0) / 1e9
-        vol = 2.0 * CELLS * Bl           # one uint16 volume, bytes per launch (one lane)
-        design_bytes = {"cost": vol, "paths": (2 * vol + 3 * vol) / 2, "wta": 2 * vol,
-                        "guided": (GUIDE_BYTES + 16 * GW * GH) * Bl}[dom_name]
+        design_bytes = design_pf * Bl
+        ncu_pf = NCU_DRAM_BYTES_PER_FRAME.get(dom_name)
         roofline = {
-            "bound": "hbm", "kernel": {"cost": "k_cost", "paths": "k_path_vert3 + k_path_lr (avg of 2 launches)",
-                                       "wta": "k_path_rl_wta", "guided": "k_guided_coeff/apply (avg of 2)"}[dom_name],
+            "bound": "hbm", "kernel": kname,
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": ncu_pf * Bl if ncu_pf else None, "peak_source": peak_src,
+            "traffic_source": "profiles/ (ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, per frame x frames per launch)",
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
             "design_bytes_per_launch": design_bytes,
             "design_gbs": design_bytes / (dom_ms / 1000.0) / 1e9,
             "design_frac": design_bytes / (dom_ms / 1000.0) / 1e9 / hbm_peak,
+            "per_kernel": {k: {"kernel": v[0], "ms_per_launch": stages.get(k, 0.0) / v[1],
+                               "design_gbs": v[2] * Bl / max(stages.get(k, 1e-9) / v[1] / 1000.0, 1e-12) / 1e9}
+                           for k, v in kernels.items()},
             "alu": {"algorithmic_iops_per_frame": ALG_IOPS, "achieved_tiops": ALG_IOPS * (value / world) / 1e12,
                     "nominal_peak_tiops": 148 * 128 * 1.965e9 / 1e12},
             "whole_step_hbm_frac_algorithmic": ALG_BYTES_FUSED * (value / world) / 1e9 / hbm_peak,

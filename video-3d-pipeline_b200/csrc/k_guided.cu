@@ -219,31 +219,14 @@ k_guided_apply(const float4* __restrict__ ab, const uint8_t* __restrict__ guide,
     out += (size_t)b * gw * gh;
     if (qout) qout += (size_t)b * gw * gh;
 
-    if (RT > 0) {
-        // all of this thread's region loads are issued before the first one is stored
-        constexpr int RWc = GT + 2 * (RT > 0 ? RT : 1);
-        constexpr int NL = (RWc * RWc + 255) / 256;
-        float4 tmp[NL];
-#pragma unroll
-        for (int k = 0; k < NL; k++) {
-            const int i = tid + k * 256;
-            if (i < RWc * RWc) {
-                const int j = i / RWc, t = i - j * RWc;
-                tmp[k] = __ldg(ab + (size_t)reflect_idx(Y0 - r + j, gh) * gw + reflect_idx(X0 - r + t, gw));
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NL; k++) {
-            const int i = tid + k * 256;
-            if (i < RWc * RWc) base[(i / RWc) * BP + (i % RWc)] = tmp[k];
-        }
-    } else {
-        for (int i = tid; i < RW * RH; i += 256) {
-            const int j = i / RW, t = i - j * RW;
-            const int X = reflect_idx(X0 - r + t, gw), Y = reflect_idx(Y0 - r + j, gh);
-            base[j * BP + t] = __ldg(ab + (size_t)Y * gw + X);
-        }
+    // region load: 16-byte cp.async (LDGSTS) straight into shared memory, all of a thread's copies in flight
+    for (int i = tid; i < RW * RH; i += 256) {
+        const int j = i / RW, t = i - j * RW;
+        const float4* src = ab + (size_t)reflect_idx(Y0 - r + j, gh) * gw + reflect_idx(X0 - r + t, gw);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(base + j * BP + t);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     for (int it = tid; it < RH * (GT / GRUN); it += 256) {
         const int j = it % RH, g = it / RH;

@@ -482,7 +482,7 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
     }
     if (!ctx->no_tma_rows) return v3d_launch_paths_horizontal(ctx, batch, st);
     {
-        V3dScope scope(ctx, ST_PATHS, st);
+        V3dScope scope(ctx, ST_LR, st);
         k_path_lr<NR, S_ACCUM, PF><<<gh, block, 0, st>>>(C, S, W1, rows, P1p, P2p);
         V3D_LAUNCHED(ctx, 1);
     }

@@ -264,7 +264,7 @@ int launch_h(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
         ctx->h_attr_set |= (1 << NR);
     }
     {
-        V3dScope scope(ctx, ST_PATHS, st);
+        V3dScope scope(ctx, ST_LR, st);
         k_path_lr_tma<NR><<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->W1, rows, P1p, P2p);
         V3D_LAUNCHED(ctx, 1);
     }

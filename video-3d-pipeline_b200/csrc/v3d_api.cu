@@ -9,7 +9,7 @@
 
 namespace {
 thread_local char g_err[512] = "";
-const char* const kStageNames[ST_COUNT] = { "split_gray", "prefilter", "cost", "paths", "wta", "select",
+const char* const kStageNames[ST_COUNT] = { "split_gray", "prefilter", "cost", "vertical", "lr", "wta", "select",
                                             "median", "speckle", "post", "guided", "copy" };
 }  // namespace
 

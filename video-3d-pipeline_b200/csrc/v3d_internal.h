@@ -9,7 +9,7 @@
 #define V3D_FULL_MASK 0xffffffffu
 
 enum V3dStage {
-    ST_SPLIT_GRAY = 0, ST_PREFILTER, ST_COST, ST_PATHS, ST_WTA, ST_SELECT, ST_MEDIAN,
+    ST_SPLIT_GRAY = 0, ST_PREFILTER, ST_COST, ST_PATHS, ST_LR, ST_WTA, ST_SELECT, ST_MEDIAN,
     ST_SPECKLE, ST_POST, ST_GUIDED, ST_COPY, ST_COUNT
 };
 

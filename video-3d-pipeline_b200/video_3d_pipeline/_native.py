@@ -17,7 +17,7 @@ V3D_EINVAL, V3D_ENOMEM, V3D_ECUDA, V3D_ESTATE = -1, -2, -3, -4
 INVALID_DISP = -16
 MODE_SGBM, MODE_HH = 0, 1
 
-STAGES = ("split_gray", "prefilter", "cost", "paths", "wta", "select", "median", "speckle", "post", "guided", "copy")
+STAGES = ("split_gray", "prefilter", "cost", "vertical", "lr", "wta", "select", "median", "speckle", "post", "guided", "copy")
 
 
 class SgbmParams(C.Structure):
