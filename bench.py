@@ -228,13 +228,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    B = args.batch
-    n_lanes = max(1, min(args.lanes, B))
-    if B % n_lanes:
-        raise ValueError("--batch must be a multiple of --lanes")
-    Bl = B // n_lanes
-    sbs_np, guide_np = synthetic_batch(Bl)
     params = nv.SgbmParams(numDisparities=D, mode=nv.MODE_SGBM)
+    n_lanes = max(1, args.lanes)
+    if args.batch > 0:
+        B = args.batch
+        if B % n_lanes:
+            raise ValueError("--batch must be a multiple of --lanes")
+        Bl = B // n_lanes
+    else:
+        # The fused vertical sweep keeps one thread-block cluster per frame co-resident; how many fit is a
+        # property of the individual GPU (GPC yield).  Size each lane's batch to exactly one such wave.
+        with nv.Context(EYE_W, EYE_H, params, max_batch=1, device=local) as probe:
+            z = torch.zeros((1, EYE_H, 2 * EYE_W, 3), dtype=torch.uint8, device=dev)
+            probe.depth_frames(z, False, want=())
+            torch.cuda.synchronize(dev)
+            Bl = probe.fused_sweep_clusters or 15
+        if world > 1:   # every rank must do the same amount of work (weak scaling): agree on the minimum
+            t = torch.tensor([Bl], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            Bl = int(t.item())
+        B = Bl * n_lanes
+    sbs_np, guide_np = synthetic_batch(Bl)
 
     class Lane:
         """One stream + context + buffers; lanes overlap each other's tails, copies and kernels."""
@@ -404,7 +418,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=45, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="frames per step per GPU (default: lanes x the co-resident clusters of the fused sweep, 45 on most B200s)")
     ap.add_argument("--lanes", type=int, default=3, help="streams/contexts the batch is split over")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -208,11 +208,15 @@ k_ccl_count(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e,
             L[i] = root;                       // flatten (roots never change after the merge kernel)
         }
     }
-    // warp-aggregate: one atomic per distinct root per warp
-    const unsigned active = __ballot_sync(V3D_FULL_MASK, root >= 0);
-    if (root >= 0) {
-        const unsigned peers = __match_any_sync(active, root);
-        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sizes[root], __popc(peers));
+    // warp-aggregate by segments of equal root among the 32 consecutive pixels: one atomic per segment
+    const int lane = threadIdx.x & 31;
+    const int prev = __shfl_up_sync(V3D_FULL_MASK, root, 1);
+    const bool head = lane == 0 || root != prev;
+    const unsigned heads = __ballot_sync(V3D_FULL_MASK, head);
+    if (head && root >= 0) {
+        const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
+        const int len = later ? __ffs(later) : 32 - lane;     // distance to the next segment head
+        atomicAdd(&sizes[root], len);
     }
 }
 
