@@ -88,146 +88,6 @@ k_path_vert(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Horizontal direction left -> right (predecessor x-1): one warp per row, accumulates into S.
-// ------------------------------------------------------------------------------------------
-template <int NR, int SMODE, int PF>
-__global__ void __launch_bounds__(256)
-k_path_lr(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, int rows,
-          uint32_t P1p, uint32_t P2p)
-{
-    using VT = typename Vec<NR>::T;
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // row over all frames
-    if (row >= rows) return;
-    const VT* C = reinterpret_cast<const VT*>(Cv) + (size_t)row * W1 * 32 + lane;
-    VT* S = reinterpret_cast<VT*>(Sv) + (size_t)row * W1 * 32 + lane;
-    VT cq[PF], sq[PF];
-#pragma unroll
-    for (int j = 0; j < PF; j++)
-        if (j < W1) { cq[j] = __ldg(C + (size_t)j * 32); if (SMODE == S_ACCUM) sq[j] = S[(size_t)j * 32]; }
-    uint32_t M[NR];
-#pragma unroll
-    for (int r = 0; r < NR; r++) M[r] = 0;
-    for (int base = 0; base < W1; base += PF) {
-#pragma unroll
-        for (int j = 0; j < PF; j++) {
-            const int i = base + j;
-            if (i >= W1) break;
-            uint32_t Cr[NR], Sr[NR], L[NR];
-            unpack<NR>(cq[j], Cr);
-            if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
-            if (i + PF < W1) {
-                cq[j] = __ldg(C + (size_t)(i + PF) * 32);
-                if (SMODE == S_ACCUM) sq[j] = S[(size_t)(i + PF) * 32];
-            }
-            path_step<NR>(M, Cr, L, P1p, P2p, lane);
-#pragma unroll
-            for (int r = 0; r < NR; r++) Sr[r] = (SMODE == S_ACCUM) ? Sr[r] + L[r] : L[r];
-            S[(size_t)i * 32] = pack<NR>(Sr);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Horizontal direction right -> left (predecessor x+1) fused with winner-takes-all: the last
-// direction, so S_total = S + L never goes back to memory.  Per pixel it emits one 8-byte record
-//   .x = minS | best << 16      (best = 0xffff when the uniqueness test rejects the pixel)
-//   .y = S[best-1] | S[best+1] << 16
-// which k_select turns into the disparity (disp2 vote, sub-pixel, LR check).
-// ------------------------------------------------------------------------------------------
-template <int NR, int PF, bool TAP_S>
-__global__ void __launch_bounds__(256)
-k_path_rl_wta(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, uint2* __restrict__ rec, int W1,
-              int rows, uint32_t P1p, uint32_t P2p, int uniq)
-{
-    using VT = typename Vec<NR>::T;
-    constexpr int D = 64 * NR;
-    __shared__ uint32_t srow[8][2][D / 2];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int row = blockIdx.x * (blockDim.x >> 5) + wib;
-    if (row >= rows) return;
-    const VT* C = reinterpret_cast<const VT*>(Cv) + (size_t)row * W1 * 32 + lane;
-    VT* S = reinterpret_cast<VT*>(Sv) + (size_t)row * W1 * 32 + lane;
-    rec += (size_t)row * W1;
-
-    // per-lane constants: disparity indices of the 2*NR values this lane holds
-    uint32_t dc[NR], idx[NR];
-#pragma unroll
-    for (int r = 0; r < NR; r++) {
-        const uint32_t d0 = 2 * NR * lane + 2 * r;
-        dc[r] = d0 | ((d0 + 1) << 8);
-        idx[r] = d0 | ((d0 + 1) << 16);
-    }
-
-    VT cq[PF], sq[PF];
-#pragma unroll
-    for (int j = 0; j < PF; j++)
-        if (j < W1) { cq[j] = __ldg(C + (size_t)(W1 - 1 - j) * 32); sq[j] = S[(size_t)(W1 - 1 - j) * 32]; }
-    uint32_t M[NR];
-#pragma unroll
-    for (int r = 0; r < NR; r++) M[r] = 0;
-    uint2 myrec = make_uint2(0, 0);
-    for (int base = 0; base < W1; base += PF) {
-#pragma unroll
-        for (int j = 0; j < PF; j++) {
-            const int i = base + j;
-            if (i >= W1) break;
-            const int x = W1 - 1 - i;
-            uint32_t Cr[NR], Sr[NR], L[NR];
-            unpack<NR>(cq[j], Cr);
-            unpack<NR>(sq[j], Sr);
-            if (i + PF < W1) {
-                cq[j] = __ldg(C + (size_t)(x - PF) * 32);
-                sq[j] = S[(size_t)(x - PF) * 32];
-            }
-            path_step<NR>(M, Cr, L, P1p, P2p, lane);
-#pragma unroll
-            for (int r = 0; r < NR; r++) Sr[r] += L[r];
-            if (TAP_S) S[(size_t)x * 32] = pack<NR>(Sr);
-
-            // ---- winner takes all: first argmin via (S << 8 | d) keys ----
-            uint32_t key = 0xffffffffu;
-#pragma unroll
-            for (int r = 0; r < NR; r++) {
-                key = min(key, __byte_perm(Sr[r], dc[r], 0x7104));
-                key = min(key, __byte_perm(Sr[r], dc[r], 0x7325));
-            }
-            key = __reduce_min_sync(V3D_FULL_MASK, key);
-            const uint32_t best = key & 0xffu, minS = key >> 8;
-            // ---- uniqueness: smallest S over |d - best| > 1 ----
-            const uint32_t off = ((1u - best) & 0xffffu) * 0x10001u;     // t = d - best + 1 in each half
-            uint32_t m2 = 0xffffffffu;
-#pragma unroll
-            for (int r = 0; r < NR; r++) {
-                const uint32_t t = __vadd2(idx[r], off);
-                const uint32_t e = __vadd2(__vminu2(t, 0x00030003u), 0xfffdfffdu);  // 0xfffd..0xffff iff t in {0,1,2}
-                m2 = __vminu2(m2, __vmaxu2(Sr[r], e));
-            }
-            m2 = __vminu2(m2, __byte_perm(m2, 0, 0x1032));
-            const uint32_t minS2 = __reduce_min_sync(V3D_FULL_MASK, m2) & 0xffffu;
-            const bool reject = minS2 * (uint32_t)(100 - uniq) < minS * 100u;
-            // ---- neighbours of the minimum, through a per-warp shared row ----
-            uint32_t* sr = srow[wib][i & 1];
-#pragma unroll
-            for (int r = 0; r < NR; r++) sr[lane * NR + r] = Sr[r];
-            __syncwarp();
-            const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sr);
-            const uint32_t sm1 = s16[best > 0 ? best - 1 : 0];
-            const uint32_t sp1 = s16[best < D - 1 ? best + 1 : D - 1];
-            if (lane == (i & 31)) {
-                myrec.x = (minS & 0xffffu) | ((reject ? 0xffffu : best) << 16);
-                myrec.y = sm1 | (sp1 << 16);
-            }
-            if ((i & 31) == 31 || i == W1 - 1) {
-                const int i0 = i & ~31;
-                if (i0 + lane <= i) rec[W1 - 1 - (i0 + lane)] = myrec;
-            }
-        }
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------
 // The three directions of one vertical sweep fused: (x, y-sy), (x-1, y-sy), (x+1, y-sy).
 // One thread-block CLUSTER of V3_CL CTAs owns a whole frame; warp g of the cluster owns the CPW
 // consecutive columns [g*CPW, (g+1)*CPW) for every row and every direction, so C is read once and
@@ -455,8 +315,6 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
     const int wpb = 8;
     dim3 block(wpb * 32);
     dim3 gv((W1 + wpb - 1) / wpb, batch);
-    const int rows = batch * H;
-    dim3 gh((rows + wpb - 1) / wpb);
     {
         V3dScope scope(ctx, ST_PATHS, st);
         // top-down sweep: predecessors (x, y-1), (x-1, y-1), (x+1, y-1)
@@ -480,21 +338,7 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
             }
         }
     }
-    if (!ctx->no_tma_rows) return v3d_launch_paths_horizontal(ctx, batch, st);
-    {
-        V3dScope scope(ctx, ST_LR, st);
-        k_path_lr<NR, S_ACCUM, PF><<<gh, block, 0, st>>>(C, S, W1, rows, P1p, P2p);
-        V3D_LAUNCHED(ctx, 1);
-    }
-    {
-        V3dScope scope(ctx, ST_WTA, st);
-        if (tap_s)
-            k_path_rl_wta<NR, PF, true><<<gh, block, 0, st>>>(C, S, ctx->rec, W1, rows, P1p, P2p, ctx->uniq);
-        else
-            k_path_rl_wta<NR, PF, false><<<gh, block, 0, st>>>(C, S, ctx->rec, W1, rows, P1p, P2p, ctx->uniq);
-        V3D_LAUNCHED(ctx, 1);
-    }
-    return V3D_OK;
+    return v3d_launch_paths_horizontal(ctx, batch, st);
 }
 
 }  // namespace

@@ -353,7 +353,6 @@ int v3d_launch_speckle(v3d_ctx* ctx, int batch, int16_t* disp, size_t dpitch, si
     if (ctx->p.speckleWindowSize <= 0) return V3D_OK;
     V3dScope scope(ctx, ST_SPECKLE, st);
     const int W = ctx->W, H = ctx->H;
-    const int n_total = batch * W * H;
     const int maxDiff = 16 * ctx->p.speckleRange;
     dim3 grid((W + 255) / 256, H, batch);
     k_ccl_rows<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H, maxDiff);

@@ -48,7 +48,6 @@ struct v3d_ctx {
     int guided_attr_set;
     int max_clusters;        // co-resident frame clusters of the fused vertical sweep (0 = not queried)
     int no_fused_vertical;
-    int no_tma_rows;         // test hook: register-prefetch horizontal kernels instead of the TMA-staged ones
     int h_attr_set;
     unsigned long long cost_attr_set;   // test hook: force the one-direction-per-launch path kernels
     std::vector<V3dTimedSpan> spans;
