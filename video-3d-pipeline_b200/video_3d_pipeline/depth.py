@@ -45,7 +45,10 @@ class HybridStereoDepthExtractor:
                  num_disparities: int = 64,
                  sgbm_mode: int = _native.MODE_SGBM,
                  num_gpus: int = 1,
-                 gpu_index: int = 0):
+                 gpu_index: int = 0,
+                 decode_threads: int = 4,
+                 png_threads: int = 8,
+                 png_compression: int = 1):
         # depth.py:33-40
         self.device = device
         self.work_dir = create_work_directory(work_dir)
@@ -59,6 +62,9 @@ class HybridStereoDepthExtractor:
         self.sgbm_mode = int(sgbm_mode)
         self.num_gpus = int(num_gpus)
         self.gpu_index = int(gpu_index)
+        self.decode_threads = int(decode_threads)      # host pipeline knobs
+        self.png_threads = int(png_threads)
+        self.png_compression = int(png_compression)    # zlib level of the 16-bit PNGs; pixels are identical
 
         if not str(device).startswith("cuda"):
             raise RuntimeError(f"device {device!r}: this build has no CPU path, use device='cuda'")
@@ -257,43 +263,97 @@ class HybridStereoDepthExtractor:
         return cache_path
 
     def _process_range(self, video_path: str, first_frame: int, count: int, cache_path: Path, index_base: int) -> int:
-        """Frames [first_frame, first_frame+count) -> depth_{index_base+i:06d}.png.  One GPU."""
-        sbs_w = sbs_h = None
-        done = 0
-        batch: List[np.ndarray] = []
-        pool = ThreadPoolExecutor(max_workers=4)      # PNG encoding releases the GIL
+        """Frames [first_frame, first_frame+count) -> depth_{index_base+i:06d}.png.  One GPU.
+
+        Host pipeline: `decode_threads` readers, each with its own cv2.VideoCapture on a
+        contiguous slice of the range, fill a bounded queue with batches; this thread feeds them to the
+        GPU; a pool encodes the PNGs.  Files carry global indices, so batch order is irrelevant.
+        """
+        import queue
+        import threading
+        bs = max(1, self.batch_size)
+        n_readers = max(1, min(int(self.decode_threads), (count + bs - 1) // bs))
+        slices = []                                    # (first frame, frame count, first output index)
+        base, extra = divmod((count + bs - 1) // bs, n_readers)
+        at = 0
+        for k in range(n_readers):
+            nb = base + (1 if k < extra else 0)
+            n = min(nb * bs, count - at)
+            if n > 0:
+                slices.append((first_frame + at, n, index_base + at))
+            at += n
+        q: "queue.Queue" = queue.Queue(maxsize=2 * len(slices))
+        stop = threading.Event()
+
+        def reader(start: int, n: int, out_index: int):
+            try:
+                batch: List[np.ndarray] = []
+                for frame in self._iter_frames(video_path, start, n):
+                    if stop.is_set():
+                        return
+                    batch.append(frame)
+                    if len(batch) == bs:
+                        q.put((out_index, batch))
+                        out_index += len(batch)
+                        batch = []
+                if batch:
+                    q.put((out_index, batch))
+            except BaseException as e:                 # surfaces in the consumer
+                q.put(e)
+            finally:
+                q.put(None)
+
+        threads = [threading.Thread(target=reader, args=sl, daemon=True) for sl in slices]
+        pool = ThreadPoolExecutor(max_workers=max(2, int(self.png_threads)))    # PNG encoding releases the GIL
         pending = []
-
-        def flush():
-            nonlocal done, sbs_w, sbs_h
-            if not batch:
-                return
-            n = len(batch)
-            h, w = batch[0].shape[:2]
-            if w % 2:
-                raise ValueError("SBS frame width must be even")
-            eye_w = w if self.unsqueeze_sbs else w // 2
-            ctx = self._context(eye_w, h, n)
-            host = torch.from_numpy(np.stack(batch)).pin_memory()
-            u16 = torch.empty((n, h, eye_w), dtype=torch.uint16).pin_memory()
-            ctx.depth_frames_host(host, self.unsqueeze_sbs, out={"u16": u16})
-            maps = u16.numpy().view(np.uint16)
-            for i in range(n):
-                path = cache_path / f"depth_{index_base + done + i:06d}.png"
-                pending.append(pool.submit(cv2.imwrite, str(path), maps[i].copy()))
-            done += n
-            print(f"✓ Saved batch depth maps ({done}/{count} total)")
-            batch.clear()
-
+        pinned = {}
+        done = 0
+        png_args = [cv2.IMWRITE_PNG_COMPRESSION, int(self.png_compression)]
         try:
-            for frame in self._iter_frames(video_path, first_frame, count):
-                batch.append(frame)
-                if len(batch) == self.batch_size:
-                    flush()
-            flush()
+            for t in threads:
+                t.start()
+            live = len(threads)
+            while live:
+                item = q.get()
+                if item is None:
+                    live -= 1
+                    continue
+                if isinstance(item, BaseException):
+                    raise item
+                out_index, batch = item
+                n = len(batch)
+                h, w = batch[0].shape[:2]
+                if w % 2:
+                    raise ValueError("SBS frame width must be even")           # depth.py:254-255
+                eye_w = w if self.unsqueeze_sbs else w // 2
+                ctx = self._context(eye_w, h, n)
+                key = (ctx.max_batch, h, w, eye_w)
+                if pinned.get("key") != key:           # pinned staging buffers are allocated once, not per batch
+                    pinned["key"] = key
+                    pinned["in"] = torch.empty((ctx.max_batch, h, w, 3), dtype=torch.uint8).pin_memory()
+                    pinned["out"] = torch.empty((ctx.max_batch, h, eye_w), dtype=torch.uint16).pin_memory()
+                host, u16 = pinned["in"][:n], pinned["out"][:n]
+                host_np = host.numpy()
+                for i, f in enumerate(batch):
+                    np.copyto(host_np[i], f)
+                ctx.depth_frames_host(host, self.unsqueeze_sbs, out={"u16": u16})
+                maps = u16.numpy().view(np.uint16)
+                for i in range(n):
+                    path = cache_path / f"depth_{out_index + i:06d}.png"
+                    pending.append(pool.submit(cv2.imwrite, str(path), maps[i].copy(), png_args))
+                done += n
+                print(f"✓ Saved batch depth maps ({done}/{count} total)")
             for f in pending:
                 f.result()
         finally:
+            stop.set()
+            while any(t.is_alive() for t in threads):          # unblock readers stuck on a full queue
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    pass
+                for t in threads:
+                    t.join(timeout=0.01)
             pool.shutdown(wait=True)
         return done
 
