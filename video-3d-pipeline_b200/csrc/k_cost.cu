@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr int TXW = 16;       // window columns per block (one warp each); TXW - 2R of them are output columns
+constexpr int TXW = 32;       // window columns per block (one warp each); TXW - 2R of them are output columns
 constexpr int PADL = 32;      // front padding (elements) of the reversed right-image rows
 
 // ---------------------------------------------------------------------------------------------
@@ -110,7 +110,7 @@ struct CostSmem {
     static constexpr int D = 64 * NR;
     static constexpr int K = 2 * R + 1;
     static constexpr int U = K >= 3 ? K : 3;
-    static constexpr int NWORDS = D / 2 + 10;
+    static constexpr int NWORDS = D / 2 + TXW / 2 + 2;
     uint4 rbuf[U][2][2][NWORDS];      // [stage][channel][copy][word] = {v, -v, lo, -hi} pairs of the right image
     uint4 lbuf[U][TXW][2];            // [stage][column][channel]     = {u, -u, lo, -hi} of the left image
     uint32_t vbuf[U][TXW][D / 2];     // [slot][column][pair]         = vertical sums

@@ -283,6 +283,11 @@ int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, kw, &cfg) == cudaSuccess) ctx->max_clusters = n;
         else cudaGetLastError();
+        if (ctx->max_clusters <= 0) {      // this device cannot co-schedule an 8-CTA cluster of this size:
+            ctx->max_clusters = 0;         // use the one-direction-per-launch kernels from now on
+            ctx->no_fused_vertical = 1;
+            return V3D_ESTATE;
+        }
     }
     V3D_CUDA(cudaLaunchKernelEx(&cfg, accum ? ka : kw, C, S, ctx->W1, ctx->H, sy, P1p, P2p));
     V3D_LAUNCHED(ctx, 1);
@@ -301,6 +306,7 @@ int try_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
     else if (need <= 7) rc = launch_vert3<(NR > 2 ? 1 : NR), 7>(ctx, batch, sy, accum, st);
     else if (need <= 8) rc = launch_vert3<(NR > 2 ? 1 : NR), 8>(ctx, batch, sy, accum, st);
     else return 0;
+    if (rc == V3D_ESTATE && ctx->no_fused_vertical) return 0;     // not schedulable here: caller falls back
     return rc ? rc : 1;
 }
 
