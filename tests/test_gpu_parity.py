@@ -227,3 +227,44 @@ def test_bad_arguments_raise():
         with pytest.raises(ValueError):
             ctx.sgbm_compute(torch.zeros((2, 20, 200), dtype=torch.uint8).cuda(),
                              torch.zeros((2, 20, 200), dtype=torch.uint8).cuda())           # batch > max_batch
+
+
+def test_two_lanes_from_two_host_threads():
+    """bench.py's lane model: one context + stream per host thread, synchronous host entry points."""
+    import threading
+    W, H, D, B = 320, 96, 64, 2
+    frames = [np.stack([synthetic.sbs_frame(40 + k, t, W, H, D) for t in range(B)]) for k in range(2)]
+    outs = [torch.empty((B, H, W), dtype=torch.int16).pin_memory() for _ in range(2)]
+    errs = []
+
+    def lane(k):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st), nv.Context(W, H, nv.SgbmParams(numDisparities=D), max_batch=B) as ctx:
+                for _ in range(3):
+                    ctx.depth_frames_host(torch.from_numpy(frames[k]).pin_memory(), False, out={"disp": outs[k]})
+        except Exception as e:          # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=lane, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    m = cv2_chain.make_matcher(D, 0)
+    for k in range(2):
+        for b in range(B):
+            l, r = cv2_chain.split_sbs_frame(frames[k][b], False)
+            assert np.array_equal(outs[k][b].numpy(), m.compute(cv2_chain.to_gray(l), cv2_chain.to_gray(r)))
+
+
+def test_fused_sweep_reports_clusters_and_matches_unfused_shapes():
+    """W1 <= 2048 and D <= 128 take the cluster-fused sweep; D = 256 takes the per-direction kernels."""
+    for (W, H, D, expect_fused) in ((400, 40, 128, True), (600, 30, 256, False)):
+        left, right, _ = synthetic.stereo_pair(8, 0, W, H, D)
+        with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=1)) as ctx:
+            d = ctx.sgbm_compute(torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda())[0].cpu().numpy()
+            assert (ctx.fused_sweep_clusters > 0) == expect_fused
+        assert np.array_equal(d, cv2_chain.make_matcher(D, 1).compute(left, right))

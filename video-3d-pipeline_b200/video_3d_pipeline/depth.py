@@ -228,8 +228,12 @@ class HybridStereoDepthExtractor:
 
     def save_depth_map(self, depth_map: np.ndarray, output_path: Path):
         """depth.py:397-406: per-frame min-max to 16 bit (on the GPU), then PNG."""
-        h, w = depth_map.shape
-        ctx = self._ctx or self._context(max(w, self.num_disparities + 8), h, 1)
+        ctx = self._ctx
+        if ctx is None:
+            # the normalisation only needs a context's min/max scratch, not a matcher-sized workspace
+            if getattr(self, "_aux_ctx", None) is None:
+                self._aux_ctx = _native.Context(72, 8, _native.SgbmParams(), max_batch=1, device=self.gpu_index)
+            ctx = self._aux_ctx
         t = torch.from_numpy(np.ascontiguousarray(depth_map, dtype=np.float32)).to(ctx.device)[None]
         u16 = ctx.normalize_u16(t)[0].cpu().numpy().view(np.uint16)
         cv2.imwrite(str(output_path), u16)
