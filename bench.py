@@ -50,12 +50,12 @@ CELLS = W1 * EYE_H * D
 ALG_IOPS = (31 + 9 * 5) * CELLS                          # 18.8 Gop
 # DRAM bytes per frame measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 15-frame launch / 15), see profiles/README.md; keyed by bench stage.
-NCU_DRAM_BYTES_PER_FRAME = {
-    "cost": (0.488135e9 + 7.374558e9) / 15,
-    "vertical": (7.432115e9 + 7.387566e9) / 15,
-    "lr": (14.863591e9 + 7.389767e9) / 15,
-    "wta": (14.864166e9 + 0.235124e9) / 15,
-    "guided": (0.435929e9 + 1.934632e9 + 2.364077e9 + 0.246581e9) / 2 / 15,
+NCU_DRAM_BYTES_PER_FRAME = {      # profiles/r01_final_ncu_full_top6.csv
+    "cost": (1.981910e9 + 7.375967e9) / 15,
+    "vertical": (7.433441e9 + 7.386856e9) / 15,
+    "lr": (14.864263e9 + 7.392594e9) / 15,
+    "wta": (14.863643e9 + 0.237814e9) / 15,
+    "guided": (0.435557e9 + 1.934585e9 + 2.363982e9 + 0.245625e9) / 2 / 15,
 }
 
 
