@@ -203,3 +203,19 @@ def test_bench_reference_arm_schema():
     assert "workload" in cfg and cfg["global_frames_per_step"] == 16
     assert bench.ALG_BYTES_DEPTH == 16588800 and bench.ALG_BYTES_FUSED == 53913600
     assert bench.ALG_IOPS == 76 * 1792 * 1080 * 128
+
+
+def test_alignment_offset_semantics(tmp_path):
+    """utils.py:299-327: the SBS clip is the time reference, the 4K clip is shifted, never below zero."""
+    import json
+    from video_3d_pipeline.utils import apply_alignment_offset, guide_start_frame
+    f = tmp_path / "alignment_data.json"
+    f.write_text(json.dumps({"video1_path": "sbs.mkv", "video2_path": "uhd.mkv", "time_offset_seconds": 1.5}))
+    assert apply_alignment_offset(str(f), "sbs.mkv", 10.0) == 10.0
+    assert apply_alignment_offset(str(f), "uhd.mkv", 10.0) == 11.5
+    assert guide_start_frame(str(f), "uhd.mkv", 24.0) == 36
+    with pytest.raises(ValueError):
+        apply_alignment_offset(str(f), "other.mkv")
+    f.write_text(json.dumps({"video1_path": "sbs.mkv", "video2_path": "uhd.mkv", "time_offset_seconds": -2.0}))
+    assert apply_alignment_offset(str(f), "uhd.mkv", 0.5) == 0.0
+    assert guide_start_frame(str(f), "uhd.mkv", 24.0) == 0

@@ -46,8 +46,16 @@ class VideoAligner:
         corr = signal.correlate(b, a, mode="full", method="fft")
         lag = int(np.argmax(corr)) - (len(a) - 1)
         peak = float(corr.max() / max(min(len(a), len(b)), 1))
-        data = {"time_offset_seconds": lag / float(rate), "sample_offset": lag, "sample_rate": int(rate),
-                "correlation_strength": peak, "sbs_video": self.sbs_video_path, "video_4k": self.video_4k_path}
+        from .utils import get_video_info
+        i1, i2 = get_video_info(self.sbs_video_path) or {}, get_video_info(self.video_4k_path) or {}
+        fps1 = float(i1.get("fps") or 0.0)
+        offset = lag / float(rate)
+        # same keys as the reference's alignment_data.json (align.py:65-76)
+        data = {"video1_path": str(self.sbs_video_path), "video2_path": str(self.video_4k_path),
+                "time_offset_seconds": float(offset), "offset_frames": float(offset * fps1) if fps1 else 0.0,
+                "correlation_strength": peak, "frame_duration": (1.0 / fps1) if fps1 else 0.0,
+                "video1_fps": fps1, "video2_fps": float(i2.get("fps") or 0.0), "sample_rate": int(rate),
+                "audio_length_analyzed": float(max_audio_length)}
         with open(self.work_dir / "alignment_data.json", "w") as f:
             json.dump(data, f, indent=2)
         return data

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .utils import get_video_info
+from .utils import get_video_info, guide_start_frame
 
 
 class SimpleDepthUpscaler:
@@ -48,7 +48,7 @@ class SimpleDepthUpscaler:
         return c
 
     def upscale_depth_maps_ffmpeg(self, depth_dir: str, target_width: int, target_height: int, output_path: str,
-                                  fps: float = 23.976, guide_video: str = None):
+                                  fps: float = 23.976, guide_video: str = None, guide_start_frame: int = 0):
         """upscale.py:21-73.  depth_%06d.png -> target size.  With `guide_video` (what
         process_depth_upscaling passes) frame i of that video guides depth map i; without it the
         upsampled depth guides itself."""
@@ -75,6 +75,8 @@ class SimpleDepthUpscaler:
             cap = cv2.VideoCapture(str(guide_video))
             if not cap.isOpened():
                 raise ValueError(f"Could not open video file: {guide_video}")
+            if guide_start_frame > 0:          # 4K frame of depth map 0 = audio alignment offset (align.py:65-76)
+                cap.set(cv2.CAP_PROP_POS_FRAMES, int(guide_start_frame))
         dev = torch.device("cuda", self.gpu_index)
         pool = ThreadPoolExecutor(max_workers=4)
         pending = []
@@ -137,9 +139,18 @@ class SimpleDepthUpscaler:
         if output_path.exists() and not force_reprocess:                      # upscale.py:104-107
             print(f"✓ Using existing depth video: {output_path}")
             return str(output_path)
+        # the alignment step leaves alignment_data.json in the work dir, next to the depth cache (run_pipeline.py:53)
+        start = 0
+        align_json = Path(depth_dir).parent / "alignment_data.json"
+        if align_json.exists():
+            try:
+                start = guide_start_frame(str(align_json), str(video_4k_path), fps or 23.976)
+                print(f"Guide frames start at 4K frame {start} (audio alignment)")
+            except (ValueError, KeyError) as e:
+                print(f"Warning: alignment data not applicable ({e}); guide starts at frame 0")
         result = self.upscale_depth_maps_ffmpeg(depth_dir=str(depth_dir), target_width=tw, target_height=th,
                                                 output_path=str(output_path), fps=fps or 23.976,
-                                                guide_video=video_4k_path)
+                                                guide_video=video_4k_path, guide_start_frame=start)
         print("✓ Depth upscaling complete!")
         print(f"  Resolution: {tw}x{th}")
         return result

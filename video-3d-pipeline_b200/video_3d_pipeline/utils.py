@@ -113,8 +113,24 @@ def extract_audio(video_path: str, output_path: str = None, sample_rate: int = 2
 
 
 def apply_alignment_offset(alignment_file: str, target_video_path: str, base_start_time: float = 0) -> float:
-    """Start time in the target video after the stored audio offset (utils.py:299-327 surface)."""
+    """Start time in `target_video_path` after the stored audio offset (utils.py:299-327): video1 (the SBS
+    clip) is the time reference, video2 (the 4K clip) is shifted by time_offset_seconds, never below 0."""
     import json
     with open(alignment_file) as f:
         data = json.load(f)
-    return max(0.0, float(base_start_time) + float(data.get("time_offset_seconds", 0.0)))
+    offset = float(data["time_offset_seconds"])
+    if str(target_video_path) == data.get("video1_path"):
+        start = float(base_start_time)
+    elif str(target_video_path) == data.get("video2_path"):
+        start = float(base_start_time) + offset
+    else:
+        raise ValueError(f"Video {target_video_path} not found in alignment data")
+    if start < 0:
+        print(f"Warning: Adjusted start time {start:.3f}s < 0, using 0")
+        start = 0.0
+    return start
+
+
+def guide_start_frame(alignment_file: str, video_4k_path: str, fps: float) -> int:
+    """First 4K frame that belongs to depth map 0: the alignment offset in frames of the 4K clip."""
+    return int(round(apply_alignment_offset(alignment_file, video_4k_path, 0.0) * float(fps)))
