@@ -109,7 +109,8 @@ template <int NR, int R>
 struct CostSmem {
     static constexpr int D = 64 * NR;
     static constexpr int K = 2 * R + 1;
-    static constexpr int U = K >= 3 ? K : 3;
+    static constexpr int RPB = (R == 2 && NR <= 2) ? 2 : 1;      // rows per block barrier
+    static constexpr int U = RPB > 1 ? 2 * K : (K >= 3 ? K : 3);
     static constexpr int NWORDS = D / 2 + TXW / 2 + 2;
     uint4 rbuf[U][2][2][NWORDS];      // [stage][channel][copy][word] = {v, -v, lo, -hi} pairs of the right image
     uint4 lbuf[U][TXW][2];            // [stage][column][channel]     = {u, -u, lo, -hi} of the left image
@@ -137,7 +138,7 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
 {
     using SM = CostSmem<NR, R>;
     constexpr int D = 64 * NR;
-    constexpr int K = SM::K, U = SM::U;
+    constexpr int K = SM::K, U = SM::U, RPB = SM::RPB;
     constexpr int TX = TXW - 2 * R;
     constexpr int NWORDS = SM::NWORDS;
     extern __shared__ __align__(128) unsigned char cost_smem[];
@@ -182,7 +183,7 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     };
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < U - 1; s++) issue(ystart + s, s);     // U-1 rows in flight
+        for (int s = 0; s < U - RPB; s++) issue(ystart + s, s);   // U-RPB rows in flight
     }
 
     uint32_t ring[K][NR];
@@ -212,10 +213,14 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     uint32_t parity = 0;
     for (int row = ystart; row < yend; row += U, parity ^= 1) {
 #pragma unroll
-        for (int ph = 0; ph < U; ph++) {
-            const int r = row + ph;
-            mbar_wait_a(bar0 + ph * 8, parity);
-            {
+        for (int pg = 0; pg < U; pg += RPB) {
+            // RPB rows between two block barriers: their cost arithmetic is independent (ILP), only the
+            // running vertical sum chains them
+#pragma unroll
+            for (int s = 0; s < RPB; s++) {
+                constexpr int dummy = 0; (void)dummy;
+                const int ph = pg + s;
+                mbar_wait_a(bar0 + ph * 8, parity);
                 const uint4 ls = l_p[ph * LSTG + 0];
                 const uint4 li = l_p[ph * LSTG + 1];
 #pragma unroll
@@ -235,19 +240,25 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
                     v_p[ph * VSTG + 32 * k] = V[k];
                 }
             }
-            __syncthreads();        // vbuf[ph] complete; every thread is done with the previous row's stage
-            if (tid == 0 && r + U - 1 < yend) issue(r + U - 1, (ph + U - 1) % U);    // refills the previous row's stage
-            const int yo = r - R;
-            if (inner && yo >= y0 && yo < y1) {
+            __syncthreads();        // vbuf slots complete; every thread is done with the previous group's stages
 #pragma unroll
-                for (int k = 0; k < NR; k++) {
-                    uint32_t acc = 0;
+            for (int s = 0; s < RPB; s++) {
+                const int ph = pg + s;
+                const int r = row + ph;
+                // refill the stage a row of the PREVIOUS group used (U - RPB rows ahead of this one)
+                if (tid == 0 && r + U - RPB < yend) issue(r + U - RPB, (ph + U - RPB) % U);
+                const int yo = r - R;
+                if (inner && yo >= y0 && yo < y1) {
 #pragma unroll
-                    for (int dx = 0; dx < K; dx++) acc += vb[ph * VSTG + nb_off[dx] + 32 * k];
-                    out[32 * k] = acc;
+                    for (int k = 0; k < NR; k++) {
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int dx = 0; dx < K; dx++) acc += vb[ph * VSTG + nb_off[dx] + 32 * k];
+                        out[32 * k] = acc;
+                    }
                 }
+                out += out_row;
             }
-            out += out_row;
         }
     }
 }
@@ -255,8 +266,8 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
 template <int NR, int R>
 int launch_cost_nr(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
-    constexpr int K = 2 * R + 1, U = K >= 3 ? K : 3;
-    const int band_h = U * 26 - 2 * R;           // band_h + 2R is a whole number of unrolled groups
+    constexpr int U = CostSmem<NR, R>::U;
+    const int band_h = U * ((130 + U - 1) / U) - 2 * R;   // band_h + 2R is a whole number of unrolled groups
     const size_t smem = sizeof(CostSmem<NR, R>) + 128;
     const int key = NR * 8 + R;
     if (!(ctx->cost_attr_set & (1ull << key))) {
