@@ -98,7 +98,9 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     if (p.mode != V3D_MODE_SGBM && p.mode != V3D_MODE_HH)
         return v3d_fail(V3D_EINVAL, "mode %d unsupported (0 = SGBM, 1 = HH)", p.mode);
     if (eye_w <= 0 || eye_h <= 0 || max_batch <= 0) return v3d_fail(V3D_EINVAL, "bad size");
-    if (eye_w > 65535) return v3d_fail(V3D_EINVAL, "eye width %d too large", eye_w);
+    if (eye_w > 8192) return v3d_fail(V3D_EINVAL, "eye width %d too large (k_select keeps a row in shared memory)", eye_w);
+    if ((long long)max_batch * eye_w * eye_h >= (1ll << 31))
+        return v3d_fail(V3D_EINVAL, "max_batch * width * height must stay below 2^31 (32-bit pixel labels)");
     if (eye_w - p.numDisparities <= p.blockSize / 2)   // cv2.error in stereosgbm.cpp
         return v3d_fail(V3D_EINVAL, "eye width %d too small for numDisparities %d (cv2 raises here)", eye_w,
                         p.numDisparities);
