@@ -97,10 +97,10 @@ k_path_vert(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, 
 // boundary and direction per row, exchanged through (distributed) shared memory behind one cluster
 // barrier per row.
 // ------------------------------------------------------------------------------------------
-constexpr int V3_CL = 8;     // CTAs per cluster (portable maximum)
-constexpr int V3_NW = 32;    // warps per CTA
+// V3_CL CTAs per cluster, V3_NW warps per CTA: 8 x 32 for D <= 128 (portable cluster size); 16 x 16 for
+// D = 256, whose 512-byte state vectors need the shared memory of 16 SMs per frame (non-portable size).
 
-template <int NR, int CPW, int SMODE>
+template <int NR, int CPW, int SMODE, int V3_CL, int V3_NW>
 __global__ void __launch_bounds__(V3_NW * 32, 1)
 k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, int H, int sy,
              uint32_t P1p, uint32_t P2p)
@@ -258,15 +258,19 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     cluster.sync();   // nobody may exit while a neighbour can still read its shared memory
 }
 
-template <int NR, int CPW>
+template <int NR, int CPW, int V3_CL, int V3_NW>
 int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
 {
     using VT = typename Vec<NR>::T;
     const size_t smem = ((size_t)3 * V3_NW * CPW * 32 + (size_t)2 * V3_NW * 2 * 32) * sizeof(VT);
-    auto kw = k_path_vert3<NR, CPW, S_WRITE>;
-    auto ka = k_path_vert3<NR, CPW, S_ACCUM>;
+    auto kw = k_path_vert3<NR, CPW, S_WRITE, V3_CL, V3_NW>;
+    auto ka = k_path_vert3<NR, CPW, S_ACCUM, V3_CL, V3_NW>;
     V3D_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     V3D_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (V3_CL > 8) {
+        V3D_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        V3D_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(V3_CL * batch);
     cfg.blockDim = dim3(V3_NW * 32);
@@ -298,14 +302,15 @@ int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
 template <int NR>
 int try_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
 {
-    if (NR > 2 || ctx->no_fused_vertical) return 0;
-    const int need = (ctx->W1 + V3_CL * V3_NW - 1) / (V3_CL * V3_NW);
+    if (ctx->no_fused_vertical) return 0;
+    constexpr int CL = NR <= 2 ? 8 : 16, NW = NR <= 2 ? 32 : 16;
+    const int need = (ctx->W1 + CL * NW - 1) / (CL * NW);
     int rc;
-    if (need <= 2) rc = launch_vert3<(NR > 2 ? 1 : NR), 2>(ctx, batch, sy, accum, st);
-    else if (need <= 4) rc = launch_vert3<(NR > 2 ? 1 : NR), 4>(ctx, batch, sy, accum, st);
-    else if (need <= 7) rc = launch_vert3<(NR > 2 ? 1 : NR), 7>(ctx, batch, sy, accum, st);
-    else if (need <= 8) rc = launch_vert3<(NR > 2 ? 1 : NR), 8>(ctx, batch, sy, accum, st);
-    else return 0;
+    if (need <= 2) rc = launch_vert3<NR, 2, CL, NW>(ctx, batch, sy, accum, st);
+    else if (need <= 4) rc = launch_vert3<NR, 4, CL, NW>(ctx, batch, sy, accum, st);
+    else if (need <= 7) rc = launch_vert3<NR, 7, CL, NW>(ctx, batch, sy, accum, st);
+    else if (need <= 8 && NR <= 2) rc = launch_vert3<NR, (NR <= 2 ? 8 : 7), CL, NW>(ctx, batch, sy, accum, st);
+    else return 0;      // wider than one cluster's shared memory: per-direction kernels
     if (rc == V3D_ESTATE && ctx->no_fused_vertical) return 0;     // not schedulable here: caller falls back
     return rc ? rc : 1;
 }
