@@ -48,7 +48,7 @@ extern "C" {
 /* cv2.StereoSGBM_create arguments, depth.py:315-325.  Field order is ABI. */
 typedef struct v3d_sgbm_params {
     int32_t minDisparity;      /* must be 0 (depth.py:316) */
-    int32_t numDisparities;    /* 64, 128 or 256 */
+    int32_t numDisparities;    /* positive multiple of 16, <= 256 (cv2's rule); kernels run at 64/128/256 */
     int32_t blockSize;         /* 5 (depth.py:318); 1,3,5,7 accepted */
     int32_t P1, P2;            /* depth.py:319-320 */
     int32_t disp12MaxDiff;     /* depth.py:321; <= 0 means 1, as in cv2 */
@@ -114,8 +114,8 @@ int v3d_sgbm_compute(v3d_ctx* ctx, const uint8_t* left_gray, const uint8_t* righ
 int v3d_set_debug_taps(v3d_ctx* ctx, int enabled);
 
 /* Parity-test taps into the workspace of the LAST v3d_sgbm_compute call.
- * which: 0 = block cost C  [batch][H][W1][D] uint16
- *        1 = aggregated S  [batch][H][W1][D] uint16 (unsaturated sum)
+ * which: 0 = block cost C  [batch][H][W1][Dk] uint16, Dk = numDisparities rounded up to 64/128/256
+ *        1 = aggregated S  [batch][H][W1][Dk] uint16 (unsaturated sum); d >= numDisparities is padding
  *        2 = raw disparity (pre-median)  [batch][H][W] int16
  *        3 = post-median, pre-speckle    [batch][H][W] int16
  * Returns a device pointer valid until the next compute/destroy. */

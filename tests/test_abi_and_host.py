@@ -48,7 +48,8 @@ def test_create_validates_before_touching_cuda():
     h = C.c_void_p()
     bad = [
         (_native.SgbmParams(numDisparities=64), 66, 20),        # W - D <= blockSize/2 : cv2.error site
-        (_native.SgbmParams(numDisparities=48), 400, 20),       # unsupported D
+        (_native.SgbmParams(numDisparities=40), 400, 20),       # not a multiple of 16 (cv2 rejects it too)
+        (_native.SgbmParams(numDisparities=272), 600, 20),      # beyond the largest kernel instantiation
         (_native.SgbmParams(minDisparity=1), 400, 20),
         (_native.SgbmParams(blockSize=4), 400, 20),
         (_native.SgbmParams(mode=2), 400, 20),

@@ -34,8 +34,8 @@ def _run_stages(W, H, D, mode, B=1, unsq=False, seed=7, **kw):
         assert np.array_equal(l[b], ol) and np.array_equal(r[b], orr), "gray"
         od, taps = osg.sgbm_compute(ol, orr, po, taps=True)
         _, Su = osg.aggregate(taps["C"], po, unsaturated=True)
-        assert np.array_equal(C[b], taps["C"]), "cost volume"
-        assert np.array_equal(S[b], Su), "aggregated S"
+        assert np.array_equal(C[b][..., :D], taps["C"]), "cost volume"      # d >= D is kernel padding
+        assert np.array_equal(S[b][..., :D], Su), "aggregated S"
         assert np.array_equal(raw[b], taps["raw"]), "raw disparity"
         assert np.array_equal(med[b], taps["median"]), "median"
         assert np.array_equal(disp[b], od), "final disparity vs oracle"
@@ -53,6 +53,13 @@ def _run_stages(W, H, D, mode, B=1, unsq=False, seed=7, **kw):
 ])
 def test_sgbm_stages_bit_exact(W, H, D, mode, B):
     _run_stages(W, H, D, mode, B)
+
+
+@pytest.mark.parametrize("W,H,D,mode", [(120, 30, 16, 0), (150, 24, 32, 1), (200, 40, 48, 0), (260, 30, 96, 0),
+                                        (300, 20, 112, 1), (400, 24, 160, 0), (420, 16, 240, 1), (90, 12, 80, 0)])
+def test_any_multiple_of_16_disparities(W, H, D, mode):
+    """cv2 accepts every positive multiple of 16; the kernels run at 64/128/256 with the rest padded."""
+    _run_stages(W, H, D, mode)
 
 
 def test_unsqueeze_path_bit_exact():
@@ -220,7 +227,7 @@ def test_bad_arguments_raise():
     with pytest.raises(ValueError):
         nv.Context(66, 20, nv.SgbmParams(numDisparities=64))       # cv2.error site
     with pytest.raises(ValueError):
-        nv.Context(200, 20, nv.SgbmParams(numDisparities=48))
+        nv.Context(200, 20, nv.SgbmParams(numDisparities=40))
     with nv.Context(200, 20, nv.SgbmParams()) as ctx:
         with pytest.raises(ValueError):
             ctx.split_gray(torch.zeros((1, 20, 401, 3), dtype=torch.uint8).cuda(), False)   # odd SBS width

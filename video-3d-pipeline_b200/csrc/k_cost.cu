@@ -131,10 +131,10 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
         "}\n" ::"r"(bar_addr), "r"(parity) : "memory");
 }
 
-template <int NR, int R>
+template <int NR, int R, bool PAD>
 __global__ void __launch_bounds__(TXW * 32)
 k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, uint32_t* __restrict__ C,
-       int W, int H, int W1, int band_h)
+       int W, int H, int W1, int band_h, int Dreal)
 {
     using SM = CostSmem<NR, R>;
     constexpr int D = 64 * NR;
@@ -155,14 +155,15 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     const int yend = ystart + nrows;
 
     // reversed element index of the strip's right-most image column, and the first staged word of each copy
-    const int Xhi = xs - R + (TXW - 1) + D;
+    // image column = window column + Dreal (the real numDisparities); d in [Dreal, D) is padding
+    const int Xhi = xs - R + (TXW - 1) + Dreal;
     const int gbase = (W - 1 - Xhi) + PADL;
     const int wlo0 = gbase >> 1, wlo1 = (gbase - 1) >> 1;
     // this warp's first element, its pair alignment and its first word inside the staged copy
     const int e0 = gbase + (TXW - 1 - c);
     const int copy = e0 & 1;
     const int wrel = ((e0 - copy) >> 1) - (copy ? wlo1 : wlo0);
-    const int Xl0 = xs - R + D;                     // image column of warp 0 in the left image
+    const int Xl0 = xs - R + Dreal;                 // image column of warp 0 in the left image
 
     if (tid == 0) {
 #pragma unroll
@@ -254,7 +255,9 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
                         uint32_t acc = 0;
 #pragma unroll
                         for (int dx = 0; dx < K; dx++) acc += vb[ph * VSTG + nb_off[dx] + 32 * k];
-                        out[32 * k] = acc;
+                        // padded disparities get a cost no real one can reach: they never win a minimum and
+                        // their path state saturates at P2, i.e. they act like the missing neighbour d = D
+                        out[32 * k] = (!PAD || 2 * (lane + 32 * k) < Dreal) ? acc : 0x20002000u;
                     }
                 }
                 out += out_row;
@@ -269,15 +272,17 @@ int launch_cost_nr(v3d_ctx* ctx, int batch, cudaStream_t st)
     constexpr int U = CostSmem<NR, R>::U;
     const int band_h = U * ((130 + U - 1) / U) - 2 * R;   // band_h + 2R is a whole number of unrolled groups
     const size_t smem = sizeof(CostSmem<NR, R>) + 128;
-    const int key = NR * 8 + R;
+    const bool pad = ctx->D != ctx->Dk;
+    const int key = (NR * 8 + R) * 2 + (pad ? 1 : 0);
+    auto kern = pad ? k_cost<NR, R, true> : k_cost<NR, R, false>;
     if (!(ctx->cost_attr_set & (1ull << key))) {
-        V3D_CUDA(cudaFuncSetAttribute(k_cost<NR, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        V3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->cost_attr_set |= (1ull << key);
     }
     const int W1 = ctx->W1, H = ctx->H;
     dim3 grid((W1 + (TXW - 2 * R) - 1) / (TXW - 2 * R), (H + band_h - 1) / band_h, batch), block(TXW * 32);
-    k_cost<NR, R><<<grid, block, smem, st>>>(ctx->rexp, ctx->rexp_wpw, ctx->lexp, reinterpret_cast<uint32_t*>(ctx->C),
-                                             ctx->W, H, W1, band_h);
+    kern<<<grid, block, smem, st>>>(ctx->rexp, ctx->rexp_wpw, ctx->lexp, reinterpret_cast<uint32_t*>(ctx->C),
+                                    ctx->W, H, W1, band_h, ctx->D);
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
@@ -316,7 +321,7 @@ int v3d_launch_prefilter(v3d_ctx* ctx, const uint8_t* left, const uint8_t* right
 int v3d_launch_cost(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     V3dScope scope(ctx, ST_COST, st);
-    switch (ctx->D) {
+    switch (ctx->Dk) {
         case 64: return launch_cost_r<1>(ctx, batch, st);
         case 128: return launch_cost_r<2>(ctx, batch, st);
         case 256: return launch_cost_r<4>(ctx, batch, st);

@@ -357,7 +357,7 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
 int v3d_launch_paths(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     const bool tap_s = ctx->debug_taps != 0;   // parity tests ask the WTA pass to also store S_total
-    switch (ctx->D) {
+    switch (ctx->Dk) {
         case 64: return launch_paths_nr<1>(ctx, batch, st, tap_s);
         case 128: return launch_paths_nr<2>(ctx, batch, st, tap_s);
         case 256: return launch_paths_nr<4>(ctx, batch, st, tap_s);

@@ -112,10 +112,10 @@ k_path_lr_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1
 // meet through two shuffle-xor steps.  That replaces two warp-wide reductions per PIXEL by two
 // 4-lane reductions per CHUNK.
 // ------------------------------------------------------------------------------------------
-template <int NR, bool TAP_S>
+template <int NR, bool TAP_S, bool PAD>
 __global__ void __launch_bounds__(HW_WARPS * 32)
 k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, uint2* __restrict__ rec, int W1,
-                  int rows, uint32_t P1p, uint32_t P2p, int uniq)
+                  int rows, uint32_t P1p, uint32_t P2p, int uniq, int Dreal)
 {
     using VT = typename Vec<NR>::T;
     constexpr int D = 64 * NR;
@@ -205,6 +205,8 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, ui
                 const int u = NR == 2 ? ((k + rot) & 3) : k;
                 v[k] = px[u];
                 const uint32_t d0 = (uint32_t)(wq * NU + u) * 8;
+                if (TAP_S && wp < n) Stap[(size_t)(lo + wp) * (STEP_B / 16) + wq * NU + u] = v[k];
+                if (PAD && (int)d0 >= Dreal) v[k] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);   // padding
                 const uint32_t dc0 = d0 | ((d0 + 1) << 8);
                 const uint32_t w[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
 #pragma unroll
@@ -212,7 +214,6 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, ui
                     const uint32_t dc = dc0 + t * 0x0202u;
                     key = __vimin3_u32(key, __byte_perm(w[t], dc, 0x7104), __byte_perm(w[t], dc, 0x7325));
                 }
-                if (TAP_S && wp < n) Stap[(size_t)(lo + wp) * (STEP_B / 16) + wq * NU + u] = v[k];
             }
             key = min(key, __shfl_xor_sync(V3D_FULL_MASK, key, 1));
             key = min(key, __shfl_xor_sync(V3D_FULL_MASK, key, 2));
@@ -257,12 +258,11 @@ int launch_h(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
     const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
     const size_t smem = (size_t)HW_WARPS * 2 * 3 * CH * 128 * NR;
     dim3 grid((rows + HW_WARPS - 1) / HW_WARPS), block(HW_WARPS * 32);
-    if (!(ctx->h_attr_set & (1 << NR))) {
-        V3D_CUDA(cudaFuncSetAttribute(k_path_lr_tma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        V3D_CUDA(cudaFuncSetAttribute(k_path_rl_wta_tma<NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        V3D_CUDA(cudaFuncSetAttribute(k_path_rl_wta_tma<NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->h_attr_set |= (1 << NR);
-    }
+    const bool pad = ctx->D != ctx->Dk;
+    auto wta = tap_s ? (pad ? k_path_rl_wta_tma<NR, true, true> : k_path_rl_wta_tma<NR, true, false>)
+                     : (pad ? k_path_rl_wta_tma<NR, false, true> : k_path_rl_wta_tma<NR, false, false>);
+    V3D_CUDA(cudaFuncSetAttribute(k_path_lr_tma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    V3D_CUDA(cudaFuncSetAttribute(wta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         V3dScope scope(ctx, ST_LR, st);
         k_path_lr_tma<NR><<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->W1, rows, P1p, P2p);
@@ -270,10 +270,7 @@ int launch_h(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
     }
     {
         V3dScope scope(ctx, ST_WTA, st);
-        if (tap_s)
-            k_path_rl_wta_tma<NR, true><<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->rec, ctx->W1, rows, P1p, P2p, ctx->uniq);
-        else
-            k_path_rl_wta_tma<NR, false><<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->rec, ctx->W1, rows, P1p, P2p, ctx->uniq);
+        wta<<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->rec, ctx->W1, rows, P1p, P2p, ctx->uniq, ctx->D);
         V3D_LAUNCHED(ctx, 1);
     }
     return V3D_OK;
@@ -284,7 +281,7 @@ int launch_h(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
 int v3d_launch_paths_horizontal(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     const bool tap_s = ctx->debug_taps != 0;   // parity tests ask the WTA pass to also store S_total
-    switch (ctx->D) {
+    switch (ctx->Dk) {
         case 64: return launch_h<1>(ctx, batch, st, tap_s);
         case 128: return launch_h<2>(ctx, batch, st, tap_s);
         case 256: return launch_h<4>(ctx, batch, st, tap_s);

@@ -91,8 +91,8 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     *out = nullptr;
     const v3d_sgbm_params& p = *params;
     if (p.minDisparity != 0) return v3d_fail(V3D_EINVAL, "minDisparity must be 0 (depth.py:316)");
-    if (p.numDisparities != 64 && p.numDisparities != 128 && p.numDisparities != 256)
-        return v3d_fail(V3D_EINVAL, "numDisparities %d unsupported (64, 128, 256)", p.numDisparities);
+    if (p.numDisparities < 16 || p.numDisparities > 256 || (p.numDisparities % 16))     // cv2: positive multiple of 16
+        return v3d_fail(V3D_EINVAL, "numDisparities %d unsupported (multiples of 16 up to 256)", p.numDisparities);
     if (p.blockSize < 1 || !(p.blockSize & 1) || p.blockSize > 7)
         return v3d_fail(V3D_EINVAL, "blockSize %d unsupported (1, 3, 5, 7)", p.blockSize);
     if (p.mode != V3D_MODE_SGBM && p.mode != V3D_MODE_HH)
@@ -127,6 +127,7 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     if (!c) return v3d_fail(V3D_ENOMEM, "host allocation failed");
     c->device = device; c->p = p;
     c->W = eye_w; c->H = eye_h; c->D = p.numDisparities; c->W1 = eye_w - c->D; c->R = p.blockSize / 2;
+    c->Dk = c->D <= 64 ? 64 : (c->D <= 128 ? 128 : 256);
     c->max_batch = max_batch; c->ndirs = ndirs;
     c->P1 = P1; c->P2 = P2;
     c->uniq = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
@@ -137,7 +138,7 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     c->rexp_wpw = v3d_rexp_words(eye_w);
 
     const size_t B = (size_t)max_batch, npx = (size_t)eye_w * eye_h;
-    const size_t vol = B * (size_t)eye_h * c->W1 * c->D * sizeof(uint16_t);
+    const size_t vol = B * (size_t)eye_h * c->W1 * c->Dk * sizeof(uint16_t);
     struct { void** p; size_t n; } allocs[] = {
         { (void**)&c->grayL, B * c->gpitch * eye_h }, { (void**)&c->grayR, B * c->gpitch * eye_h },
         { (void**)&c->rexp, B * eye_h * 4 * (size_t)c->rexp_wpw * sizeof(uint4) },
@@ -291,7 +292,7 @@ int v3d_debug_tap(v3d_ctx* ctx, int which, void** dev_ptr, size_t* bytes)
     if (!ctx->debug_taps && (which == 1 || which == 3))
         return v3d_fail(V3D_ESTATE, "tap %d needs v3d_set_debug_taps(ctx, 1) before the compute call", which);
     const size_t B = (size_t)ctx->last_batch;
-    const size_t vol = B * (size_t)ctx->H * ctx->W1 * ctx->D * sizeof(uint16_t);
+    const size_t vol = B * (size_t)ctx->H * ctx->W1 * ctx->Dk * sizeof(uint16_t);
     const size_t img = B * (size_t)ctx->W * ctx->H * sizeof(int16_t);
     switch (which) {
         case 0: *dev_ptr = ctx->C; *bytes = vol; return V3D_OK;

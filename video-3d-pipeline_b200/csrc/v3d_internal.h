@@ -19,6 +19,7 @@ struct v3d_ctx {
     int device;
     v3d_sgbm_params p;
     int W, H, D, W1, R, max_batch, ndirs;
+    int Dk;                      // disparities the kernels are instantiated for (64/128/256 >= D); d in [D, Dk) is padding
     int P1, P2, uniq, maxdiff, ftzero;
 
     // workspace (device)

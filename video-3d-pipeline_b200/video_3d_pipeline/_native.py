@@ -130,6 +130,7 @@ class Context:
         require_cuda()
         self.params = params or SgbmParams()
         self.W, self.H, self.D = int(eye_w), int(eye_h), int(self.params.numDisparities)
+        self.Dk = 64 if self.D <= 64 else (128 if self.D <= 128 else 256)    # kernel disparity count (padded)
         self.max_batch = int(max_batch)
         self.device = torch.device("cuda", int(device))
         self._h = C.c_void_p()
@@ -218,7 +219,7 @@ class Context:
     def debug_tap(self, which, batch):
         """Copy of a workspace volume of the last compute call (parity tests only)."""
         W1 = self.W - self.D
-        shape, dt = {0: ((batch, self.H, W1, self.D), torch.int16), 1: ((batch, self.H, W1, self.D), torch.int16),
+        shape, dt = {0: ((batch, self.H, W1, self.Dk), torch.int16), 1: ((batch, self.H, W1, self.Dk), torch.int16),
                      2: ((batch, self.H, self.W), torch.int16), 3: ((batch, self.H, self.W), torch.int16)}[which]
         out = torch.empty(shape, dtype=dt, device=self.device)
         _check(lib().v3d_debug_tap_copy(self._h, which, out.data_ptr(), out.numel() * out.element_size(),
