@@ -15,6 +15,7 @@ namespace {
 
 constexpr int GT = 32;      // tile edge
 constexpr int GRUN = 8;     // outputs per thread along the filtered axis (first direct, the rest slid)
+constexpr int GRUNV = 4;    // run length of the vertical pass: shorter runs keep all 256 threads of a tile busy
 constexpr int GRMAX = 8;    // largest supported radius
 
 __device__ __forceinline__ int reflect_idx(int i, int n)
@@ -155,9 +156,9 @@ k_guided_coeff(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* 
     __syncthreads();
 
     // vertical box sums + 3x3 solve: item = (column, run of GRUN output rows)
-    if (tid < GT * (GT / GRUN)) {
+    if (tid < GT * (GT / GRUNV)) {
         const int col = tid & 31, rg = tid >> 5;
-        const float* hc = hs + (size_t)(rg * GRUN) * HP + col;
+        const float* hc = hs + (size_t)(rg * GRUNV) * HP + col;
         float acc[13];
 #pragma unroll
         for (int q = 0; q < 13; q++) acc[q] = 0.0f;
@@ -169,13 +170,13 @@ k_guided_coeff(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* 
         const float inv_n = 1.0f / (float)((2 * r + 1) * (2 * r + 1));
         const int X = X0 + col;
 #pragma unroll 1
-        for (int o = 0; o < GRUN; o++) {
+        for (int o = 0; o < GRUNV; o++) {
             if (o > 0) {
 #pragma unroll
                 for (int q = 0; q < 13; q++)
                     acc[q] += hc[((size_t)q * RH + o + 2 * r) * HP] - hc[((size_t)q * RH + o - 1) * HP];
             }
-            const int Y = Y0 + rg * GRUN + o;
+            const int Y = Y0 + rg * GRUNV + o;
             if (X >= gw || Y >= gh) continue;
             float m[13];
 #pragma unroll
@@ -240,18 +241,18 @@ k_guided_apply(const float4* __restrict__ ab, const uint8_t* __restrict__ guide,
         for (int o = 1; o < GRUN; o++) { add4(acc, row[o + 2 * r]); sub4(acc, row[o - 1]); o4[o] = acc; }
     }
     __syncthreads();
-    if (tid < GT * (GT / GRUN)) {
+    if (tid < GT * (GT / GRUNV)) {
         const int col = tid & 31, rg = tid >> 5;
-        const float4* hc = hs + (rg * GRUN) * HP + col;
+        const float4* hc = hs + (rg * GRUNV) * HP + col;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
         for (int t = 0; t <= 2 * r; t++) add4(acc, hc[t * HP]);
         const float inv_n = 1.0f / (float)((2 * r + 1) * (2 * r + 1));
         const int X = X0 + col;
 #pragma unroll
-        for (int o = 0; o < GRUN; o++) {
+        for (int o = 0; o < GRUNV; o++) {
             if (o > 0) { add4(acc, hc[(o + 2 * r) * HP]); sub4(acc, hc[(o - 1) * HP]); }
-            const int Y = Y0 + rg * GRUN + o;
+            const int Y = Y0 + rg * GRUNV + o;
             if (X >= gw || Y >= gh) continue;
             const float3 I = load_guide(guide, gw, X, Y);
             const float q = (acc.x * (I.x - 0.5f) + acc.y * (I.y - 0.5f) + acc.z * (I.z - 0.5f) + acc.w) * inv_n;
