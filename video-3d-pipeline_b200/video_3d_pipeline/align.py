@@ -6,7 +6,6 @@ needs the ffmpeg binary for audio extraction and raises a clear error when that 
 """
 import json
 import wave
-from pathlib import Path
 from typing import Dict
 
 import numpy as np
