@@ -136,3 +136,39 @@ def test_guided_oracle_building_blocks():
     q32, o32 = guided.guided_upscale_cv2(synthetic.depth_u16(1, 0, 96, 54), gd)
     assert np.abs(q64 - q32).max() * 65535 < 0.5
     assert np.abs(o64.astype(np.int64) - o32.astype(np.int64)).max() <= 1
+
+
+def test_guided_oracle_matches_bruteforce_definition():
+    """The guided-upscale oracle has no reference to pin it (upstream ships no guided filter), so it is
+    at least checked against an independent, literal evaluation of He/Sun/Tang eq. (19)-(21): per-pixel
+    window loops over a symmetric-padded image and np.linalg.solve, no separable / cumulative sums."""
+    rng = np.random.default_rng(7)
+    h, w, r, eps = 9, 11, 2, 1e-3
+    depth = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+    guide = rng.integers(0, 256, (2 * h, 2 * w, 3), dtype=np.uint8)
+    q, out = guided.guided_upscale(depth, guide, r, eps)
+
+    H, W = guide.shape[:2]
+    p = guided.bilinear_upsample(depth.astype(np.float64) / 65535.0, H, W)
+    I = guide.astype(np.float64) / 255.0
+    pad = lambda a: np.pad(a, [(r, r), (r, r)] + [(0, 0)] * (a.ndim - 2), mode="symmetric")
+    Ip, pp = pad(I), pad(p)
+    a = np.zeros((H, W, 3))
+    b = np.zeros((H, W))
+    for y in range(H):
+        for x in range(W):
+            wi = Ip[y:y + 2 * r + 1, x:x + 2 * r + 1].reshape(-1, 3)
+            wp = pp[y:y + 2 * r + 1, x:x + 2 * r + 1].reshape(-1)
+            mu, pbar = wi.mean(0), wp.mean()
+            sigma = (wi - mu).T @ (wi - mu) / len(wp)
+            cov = ((wi - mu) * (wp - pbar)[:, None]).mean(0)
+            a[y, x] = np.linalg.solve(sigma + eps * np.eye(3), cov)
+            b[y, x] = pbar - a[y, x] @ mu
+    ap, bp = pad(a), pad(b)
+    q_ref = np.zeros((H, W))
+    for y in range(H):
+        for x in range(W):
+            abar = ap[y:y + 2 * r + 1, x:x + 2 * r + 1].reshape(-1, 3).mean(0)
+            q_ref[y, x] = abar @ I[y, x] + bp[y:y + 2 * r + 1, x:x + 2 * r + 1].mean()
+    assert np.abs(q - q_ref).max() < 1e-9
+    assert np.array_equal(out, np.floor(np.clip(q_ref, 0, 1) * 65535 + 0.5).astype(np.uint16))
