@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "video-3d-pipeline_b200"))
 import cv2, numpy as np
 
-def main(n=64):
+def main(n=64, decode_threads=4):
     from video_3d_pipeline import synthetic
     from video_3d_pipeline.depth import IGEVStereoDepthExtractor
     tmp = Path(tempfile.mkdtemp(prefix="v3d_mod_"))
@@ -35,13 +35,14 @@ def main(n=64):
     for i in range(8): cv2.imwrite(str(tmp / f"p{i}.png"), img)
     t_png = (time.perf_counter() - t0) / 8
     ex = IGEVStereoDepthExtractor(work_dir=str(tmp / "w"), cache_dir=str(tmp / "w"), unsqueeze_sbs=False,
-                                  batch_size=16, stereo_only=True, num_disparities=128)
+                                  batch_size=16, stereo_only=True, num_disparities=128,
+                                  decode_threads=decode_threads)
     ex.process_video_sbs(str(clip), max_frames=16, force_reprocess=True)        # warm-up (context, kernels)
     t0 = time.perf_counter()
     out = ex.process_video_sbs(str(clip), force_reprocess=True)
     wall = time.perf_counter() - t0
-    print(json.dumps({"frames": k, "module_path_fps": round(k / wall, 1), "decode_only_fps": round(k / t_dec, 1),
+    print(json.dumps({"decode_threads": decode_threads, "frames": k, "module_path_fps": round(k / wall, 1), "decode_only_fps": round(k / t_dec, 1),
                       "png16_encode_ms_per_frame_one_core": round(t_png * 1000, 1), "out_dir_files": len(list(out.glob('*.png')))}))
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 64)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 64, int(sys.argv[2]) if len(sys.argv) > 2 else 4)
