@@ -49,3 +49,44 @@ def test_random_shapes_and_parameters_match_cv2(seed):
     with ctx:
         got = ctx.sgbm_compute(torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda())[0].cpu().numpy()
     assert np.array_equal(got, ref), dict(D=D, mode=mode, W=W, H=H, kind=kind, **kw)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_guided_upscale_shapes(seed):
+    """Arbitrary (non-integer) scale factors, radii and eps.  At the configured eps = 1e-3 (and above) the
+    fp32 kernels stay within the north-star budget, |q - oracle| < 0.5 LSB16 and uint16 within 1.  The filter
+    gain grows like 1/sqrt(eps), so for eps = 1e-4 the fp32 budget is stated (and tested) as 2 LSB16."""
+    from oracle import guided as og
+    rng = np.random.default_rng(500 + seed)
+    w, h = int(rng.integers(20, 160)), int(rng.integers(20, 120))
+    gw, gh = int(rng.integers(max(w, 33), 3 * w)), int(rng.integers(max(h, 33), 3 * h))
+    r = int(rng.integers(1, 9))
+    eps = float(rng.choice([1e-4, 1e-3, 1e-2]))
+    depth = synthetic.depth_u16(seed, 0, w, h)
+    if seed % 3 == 0:       # hard depth edges
+        depth[:, w // 2:] = 65535 - depth[:, w // 2:]
+    guide = synthetic.guide_frame(seed, 0, gw, gh)
+    with nv.Context(80, 8, nv.SgbmParams()) as ctx:
+        out, q = ctx.guided_upscale(torch.from_numpy(depth.view(np.int16))[None].cuda().view(torch.uint16),
+                                    torch.from_numpy(guide)[None].cuda(), r, eps, want_q=True)
+        out, q = out[0].cpu().numpy().view(np.uint16), q[0].cpu().numpy()
+    oq, ou = og.guided_upscale(depth, guide, r, eps)
+    lsb = 0.5 if eps >= 1e-3 else 2.0
+    err = float(np.abs(q - oq).max()) * 65535
+    assert err < lsb, dict(w=w, h=h, gw=gw, gh=gh, r=r, eps=eps, err_lsb16=err)
+    assert np.abs(out.astype(np.int64) - ou.astype(np.int64)).max() <= (1 if eps >= 1e-3 else 2)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_split_gray_unsqueeze(seed):
+    from oracle import sgbm as osg
+    rng = np.random.default_rng(900 + seed)
+    h, half = int(rng.integers(1, 40)), int(rng.integers(70, 400))
+    frame = rng.integers(0, 256, (2, h, 2 * half, 3), dtype=np.uint8)
+    for uns in (False, True):
+        We = 2 * half if uns else half
+        with nv.Context(max(We, 80), h, nv.SgbmParams(), max_batch=2) as ctx:
+            l, r = ctx.split_gray(torch.from_numpy(frame).cuda(), uns)
+        for b in range(2):
+            ol, orr = osg.split_gray(frame[b], uns)
+            assert np.array_equal(l[b].cpu().numpy(), ol) and np.array_equal(r[b].cpu().numpy(), orr)
