@@ -10,6 +10,7 @@
 // Moments are taken about a per-tile centre (box sums are shift-covariant) so the covariance
 // subtraction does not cancel.
 #include "v3d_internal.h"
+#include <cstdlib>
 
 namespace {
 
@@ -263,6 +264,357 @@ k_guided_apply(const float4* __restrict__ ab, const uint8_t* __restrict__ guide,
     }
 }
 
+// ================================================================================================
+// Streaming variant: a CTA owns a strip of TW output columns (NT = TW + 2r region columns, one thread
+// each) and walks down a segment of rows.  Vertical box sums live in registers as running sums
+// (enter the new row, leave the row 2r+1 above, which a (2r+1)-row ring in shared memory remembers);
+// every R rows the column sums go through shared memory once for the horizontal pass.
+//   * guide moments are kept in BYTE units about an integer centre: I, I.I sums are integers below
+//     2^24, so fp32 adds them exactly -- no drift however long the strip;
+//   * the four planes that involve the depth (p, I.p) are compensated (Kahan) running sums, so their
+//     error stays that of one direct 17-term sum; the horizontal pass slides over runs of GR only.
+struct RowTap { int gy, y0, y1; float fy; };
+
+__device__ __forceinline__ float u16f(uint32_t v) { return __uint_as_float(0x4b000000u | v) - 8388608.0f; }
+// byte k of `w` as 8388608 + byte (one PRMT); subtract (8388608 + centre) to get the centred value exactly
+template <int K> __device__ __forceinline__ float byte_magic(uint32_t w)
+{
+    return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7540 | K));
+}
+__device__ __forceinline__ void kahan(float& v, float& c, float d)
+{
+    const float y = __fsub_rn(d, c), t = __fadd_rn(v, y);
+    c = __fsub_rn(__fsub_rn(t, v), y);
+    v = t;
+}
+
+template <int RT, int NT, int R, int GR>
+__global__ void __launch_bounds__(NT, 512 / NT)
+k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* __restrict__ guide, int gw, int gh,
+                 int r_arg, float eps, int seg, float4* __restrict__ ab)
+{
+    extern __shared__ float4 gsm[];
+    const int r = RT > 0 ? RT : r_arg, win = 2 * r + 1;
+    const int TW = (NT - 2 * r) & ~7;
+    constexpr int VP = NT + NT / GR + 1;                            // float4 slots per (plane group, row)
+    float4* vbuf = gsm;                                             // [4 plane groups][R][VP], column x at x + x/GR
+    uint2* ring = reinterpret_cast<uint2*>(gsm + 4 * R * VP);       // [win][NT] {rgb bytes, p - centre}
+    __shared__ RowTap taps[2][R];
+    __shared__ float centre_p;
+    __shared__ uint32_t centre_rgb;
+    const int tid = threadIdx.x;
+    const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * seg, b = blockIdx.z;
+    const int seg_h = min(seg, gh - Y0), nrows = seg_h + 2 * r;
+    depth += (size_t)b * w * h;
+    guide += (size_t)b * gw * gh * 3;
+    ab += (size_t)b * gw * gh;
+    const float s16 = 1.0f / 65535.0f, k255 = 1.0f / 255.0f;
+
+    const int gx = reflect_idx(X0 - r + tid, gw);
+    int x0, x1;
+    float fx;
+    axis_tap(gx, w, gw, x0, x1, fx);
+    auto rowlerp = [&](int y) -> float {
+        const uint16_t* rp = depth + (size_t)y * w;
+        return u16f(__ldg(rp + x0)) * s16 * (1.0f - fx) + u16f(__ldg(rp + x1)) * s16 * fx;
+    };
+    auto make_tap = [&](int j) -> RowTap {
+        RowTap t;
+        t.gy = reflect_idx(Y0 - r + j, gh);
+        axis_tap(t.gy, h, gh, t.y0, t.y1, t.fy);
+        return t;
+    };
+    if (tid < R) taps[0][tid] = make_tap(tid);
+    if (tid == NT / 2) {                                            // strip centre: column X0 + TW/2, middle row
+        const int Yc = min(Y0 + seg_h / 2, gh - 1);
+        int y0, y1;
+        float fy;
+        axis_tap(Yc, h, gh, y0, y1, fy);
+        const uint8_t* gp = guide + ((size_t)Yc * gw + gx) * 3;
+        centre_rgb = (uint32_t)__ldg(gp) | ((uint32_t)__ldg(gp + 1) << 8) | ((uint32_t)__ldg(gp + 2) << 16);
+        centre_p = rowlerp(y0) * (1.0f - fy) + rowlerp(y1) * fy;
+    }
+    __syncthreads();
+    const uint32_t crgb = centre_rgb;
+    const float cp = centre_p;
+    const float cb0 = 8388608.0f + (float)(crgb & 0xff), cb1 = 8388608.0f + (float)((crgb >> 8) & 0xff),
+                cb2 = 8388608.0f + (float)((crgb >> 16) & 0xff);
+    for (int k = 0; k < win; k++) ring[k * NT + tid] = make_uint2(crgb, 0u);   // centre pixel: all moments 0
+
+    float V[13], C[4];
+#pragma unroll
+    for (int q = 0; q < 13; q++) V[q] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) C[q] = 0.0f;
+    int cy0 = -1, cy1 = -1, rslot = 0;
+    float ctop = 0.0f, cbot = 0.0f;
+    const int wslot = tid + tid / GR;
+    const int runs = TW / GR;
+    const float inv_n = 1.0f / (float)(win * win);
+    const uint8_t* gcol = guide + (size_t)gx * 3;
+
+    for (int g = 0; g * R < nrows; g++) {
+        const RowTap* tp = taps[g & 1];
+        uint32_t rgbv[R];
+#pragma unroll
+        for (int jj = 0; jj < R; jj++) {                            // all guide loads of the group in flight first
+            if (g * R + jj < nrows) {
+                const uint8_t* gp = gcol + (size_t)tp[jj].gy * gw * 3;
+                rgbv[jj] = (uint32_t)__ldg(gp) | ((uint32_t)__ldg(gp + 1) << 8) | ((uint32_t)__ldg(gp + 2) << 16);
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < R; jj++) {
+            const int j = g * R + jj;
+            if (j >= nrows) break;
+            const RowTap rt = tp[jj];
+            const uint32_t rgb = rgbv[jj];
+            float nt, nb;
+            if (rt.y0 == cy0) nt = ctop; else if (rt.y0 == cy1) nt = cbot; else nt = rowlerp(rt.y0);
+            if (rt.y1 == cy1) nb = cbot; else if (rt.y1 == cy0) nb = ctop; else nb = rowlerp(rt.y1);
+            cy0 = rt.y0; cy1 = rt.y1; ctop = nt; cbot = nb;
+            const float ap = nt * (1.0f - rt.fy) + nb * rt.fy - cp;
+            uint2* slot = ring + rslot * NT + tid;
+            rslot = (rslot + 1 == win) ? 0 : rslot + 1;
+            const uint2 old = *slot;
+            *slot = make_uint2(rgb, __float_as_uint(ap));
+            const float a0 = byte_magic<0>(rgb) - cb0, a1 = byte_magic<1>(rgb) - cb1, a2 = byte_magic<2>(rgb) - cb2;
+            const float b0 = byte_magic<0>(old.x) - cb0, b1 = byte_magic<1>(old.x) - cb1, b2 = byte_magic<2>(old.x) - cb2;
+            const float bp = __uint_as_float(old.y);
+            // exact planes (integers): I, I.I
+            V[0] += a0 - b0; V[1] += a1 - b1; V[2] += a2 - b2;
+            V[7] += fmaf(a0, a0, -(b0 * b0));  V[8] += fmaf(a0, a1, -(b0 * b1));  V[9] += fmaf(a0, a2, -(b0 * b2));
+            V[10] += fmaf(a1, a1, -(b1 * b1)); V[11] += fmaf(a1, a2, -(b1 * b2)); V[12] += fmaf(a2, a2, -(b2 * b2));
+            // depth planes: compensated
+            kahan(V[3], C[0], ap - bp);
+            kahan(V[4], C[1], fmaf(a0, ap, -(b0 * bp)));
+            kahan(V[5], C[2], fmaf(a1, ap, -(b1 * bp)));
+            kahan(V[6], C[3], fmaf(a2, ap, -(b2 * bp)));
+            if (j >= 2 * r) {
+                float4* vr = vbuf + jj * VP + wslot;
+                vr[0] = make_float4(V[0], V[1], V[2], V[3]);
+                vr[R * VP] = make_float4(V[4], V[5], V[6], V[7]);
+                vr[2 * R * VP] = make_float4(V[8], V[9], V[10], V[11]);
+                reinterpret_cast<float*>(vr + 3 * R * VP)[0] = V[12];
+            }
+        }
+        if (tid < R) taps[(g + 1) & 1][tid] = make_tap((g + 1) * R + tid);
+        __syncthreads();
+
+        // horizontal pass + 3x3 solve: item = (row of the group, run of GR output columns)
+        for (int it = tid; it < R * runs; it += NT) {
+            const int jj = it / runs, run = it - jj * runs;
+            const int o = g * R + jj - 2 * r;
+            const int xb = run * GR;
+            if (o < 0 || o >= seg_h || X0 + xb >= gw) continue;
+            const float4* vr = vbuf + jj * VP + xb + run;          // window start; xb is a multiple of GR
+            float acc[13], m[13];
+            auto ld13 = [&](int dx) {                               // dx = offset from the window start
+                const float4* e = vr + (RT > 0 ? dx + dx / GR : (xb + dx) + (xb + dx) / GR - xb - run);
+                const float4 g0 = e[0], g1 = e[R * VP], g2 = e[2 * R * VP];
+                m[0] = g0.x; m[1] = g0.y; m[2] = g0.z; m[3] = g0.w;
+                m[4] = g1.x; m[5] = g1.y; m[6] = g1.z; m[7] = g1.w;
+                m[8] = g2.x; m[9] = g2.y; m[10] = g2.z; m[11] = g2.w;
+                m[12] = reinterpret_cast<const float*>(e + 3 * R * VP)[0];
+            };
+#pragma unroll
+            for (int q = 0; q < 13; q++) acc[q] = 0.0f;
+            if (RT > 0) {
+                const float4* v0 = vr;
+#pragma unroll 1
+                for (int t0 = 0; t0 + GR <= 2 * RT + 1; t0 += GR, vr += GR + 1) {   // whole runs: pad advances with them
+#pragma unroll
+                    for (int t = 0; t < GR; t++) {
+                        ld13(t);
+#pragma unroll
+                        for (int q = 0; q < 13; q++) acc[q] += m[q];
+                    }
+                }
+                vr = v0;
+#pragma unroll
+                for (int t = (2 * RT + 1) / GR * GR; t <= 2 * RT; t++) {
+                    ld13(t);
+#pragma unroll
+                    for (int q = 0; q < 13; q++) acc[q] += m[q];
+                }
+            } else {
+#pragma unroll 1
+                for (int t = 0; t <= 2 * r; t++) {
+                    ld13(t);
+#pragma unroll
+                    for (int q = 0; q < 13; q++) acc[q] += m[q];
+                }
+            }
+            const size_t orow = (size_t)(Y0 + o) * gw;
+            const float kn = k255 * inv_n, kkn = k255 * k255 * inv_n;
+            const float cI0 = (float)(crgb & 0xff) * k255 - 0.5f, cI1 = (float)((crgb >> 8) & 0xff) * k255 - 0.5f,
+                        cI2 = (float)((crgb >> 16) & 0xff) * k255 - 0.5f;
+#pragma unroll
+            for (int o2 = 0; o2 < GR; o2++) {
+                if (o2 > 0) {
+                    ld13(o2 + 2 * r);
+#pragma unroll
+                    for (int q = 0; q < 13; q++) acc[q] += m[q];
+                    ld13(o2 - 1);
+#pragma unroll
+                    for (int q = 0; q < 13; q++) acc[q] -= m[q];
+                }
+                const int X = X0 + xb + o2;
+                if (X >= gw) break;
+                const float mI0 = acc[0] * kn, mI1 = acc[1] * kn, mI2 = acc[2] * kn, mp = acc[3] * inv_n;
+                const float c0 = acc[4] * kn - mI0 * mp, c1 = acc[5] * kn - mI1 * mp, c2 = acc[6] * kn - mI2 * mp;
+                const float s00 = acc[7] * kkn - mI0 * mI0 + eps, s01 = acc[8] * kkn - mI0 * mI1, s02 = acc[9] * kkn - mI0 * mI2;
+                const float s11 = acc[10] * kkn - mI1 * mI1 + eps, s12 = acc[11] * kkn - mI1 * mI2, s22 = acc[12] * kkn - mI2 * mI2 + eps;
+                const float k00 = s11 * s22 - s12 * s12, k01 = s02 * s12 - s01 * s22, k02 = s01 * s12 - s02 * s11;
+                const float k11 = s00 * s22 - s02 * s02, k12 = s01 * s02 - s00 * s12, k22 = s00 * s11 - s01 * s01;
+                const float det = s00 * k00 + s01 * k01 + s02 * k02;
+                const float idet = __fdiv_rn(1.0f, det);
+                const float a0 = (k00 * c0 + k01 * c1 + k02 * c2) * idet;
+                const float a1 = (k01 * c0 + k11 * c1 + k12 * c2) * idet;
+                const float a2 = (k02 * c0 + k12 * c1 + k22 * c2) * idet;
+                // b referred to a guide centred at 0.5:  q = a.(I - 0.5) + b
+                const float bb = (mp + cp) - a0 * (mI0 + cI0) - a1 * (mI1 + cI1) - a2 * (mI2 + cI2);
+                ab[orow + X] = make_float4(a0, a1, a2, bb);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int RT, int NT, int R, int GR>
+__global__ void __launch_bounds__(NT)
+k_guided_apply_s(const float4* __restrict__ ab, const uint8_t* __restrict__ guide, int gw, int gh, int r_arg, int seg,
+                 int vec_ok, uint16_t* __restrict__ out, float* __restrict__ qout)
+{
+    extern __shared__ float4 gsm[];
+    const int r = RT > 0 ? RT : r_arg, win = 2 * r + 1;
+    const int TW = (NT - 2 * r) & ~7;
+    constexpr int VP = NT + NT / GR + 1;
+    float4* vbuf = gsm;                  // [R][VP]
+    float4* ring = gsm + R * VP;         // [win][NT]
+    __shared__ int rows[2][R];
+    const int tid = threadIdx.x;
+    const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * seg, b = blockIdx.z;
+    const int seg_h = min(seg, gh - Y0), nrows = seg_h + 2 * r;
+    ab += (size_t)b * gw * gh;
+    guide += (size_t)b * gw * gh * 3;
+    out += (size_t)b * gw * gh;
+    if (qout) qout += (size_t)b * gw * gh;
+    const int gx = reflect_idx(X0 - r + tid, gw);
+    for (int k = 0; k < win; k++) ring[k * NT + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < R) rows[0][tid] = reflect_idx(Y0 - r + tid, gh);
+    __syncthreads();
+    float4 V = make_float4(0.f, 0.f, 0.f, 0.f), C = V;
+    int rslot = 0;
+    const int runs = TW / GR;
+    const float inv_n = 1.0f / (float)(win * win), k255 = 1.0f / 255.0f;
+    const int wslot = tid + tid / GR;
+
+    for (int g = 0; g * R < nrows; g++) {
+        const int* rw = rows[g & 1];
+        float4 nv[R];
+#pragma unroll
+        for (int jj = 0; jj < R; jj++)
+            if (g * R + jj < nrows) nv[jj] = __ldg(ab + (size_t)rw[jj] * gw + gx);
+#pragma unroll
+        for (int jj = 0; jj < R; jj++) {
+            const int j = g * R + jj;
+            if (j >= nrows) break;
+            float4* slot = ring + rslot * NT + tid;
+            rslot = (rslot + 1 == win) ? 0 : rslot + 1;
+            const float4 old = *slot;
+            *slot = nv[jj];
+            kahan(V.x, C.x, nv[jj].x - old.x); kahan(V.y, C.y, nv[jj].y - old.y);
+            kahan(V.z, C.z, nv[jj].z - old.z); kahan(V.w, C.w, nv[jj].w - old.w);
+            if (j >= 2 * r) vbuf[jj * VP + wslot] = V;
+        }
+        if (tid < R) rows[(g + 1) & 1][tid] = reflect_idx(Y0 - r + (g + 1) * R + tid, gh);
+        __syncthreads();
+
+        for (int it = tid; it < R * runs; it += NT) {
+            const int jj = it / runs, run = it - jj * runs;
+            const int o = g * R + jj - 2 * r;
+            const int xb = run * GR, X = X0 + xb;
+            if (o < 0 || o >= seg_h || X >= gw) continue;
+            const int Y = Y0 + o;
+            const float4* vr = vbuf + jj * VP + xb + run;          // window start; xb is a multiple of GR
+            auto at = [&](int dx) -> float4 { return vr[RT > 0 ? dx + dx / GR : (xb + dx) + (xb + dx) / GR - xb - run]; };
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RT > 0) {
+#pragma unroll
+                for (int t = 0; t <= 2 * RT; t++) add4(acc, at(t));
+            } else {
+#pragma unroll 1
+                for (int t = 0; t <= 2 * r; t++) add4(acc, at(t));
+            }
+            const size_t base = (size_t)Y * gw + X;
+            const bool vec = vec_ok && GR == 8 && X + GR <= gw;
+            uint32_t gbytes[6];
+            if (vec) {
+                const uint2* gp = reinterpret_cast<const uint2*>(guide + base * 3);
+                const uint2 u0 = __ldg(gp), u1 = __ldg(gp + 1), u2 = __ldg(gp + 2);
+                gbytes[0] = u0.x; gbytes[1] = u0.y; gbytes[2] = u1.x; gbytes[3] = u1.y; gbytes[4] = u2.x; gbytes[5] = u2.y;
+            }
+            uint32_t packed[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int o2 = 0; o2 < GR; o2++) {
+                if (o2 > 0) { add4(acc, at(o2 + 2 * r)); sub4(acc, at(o2 - 1)); }
+                if (X + o2 >= gw) break;
+                float I0, I1, I2;
+                if (vec) {
+                    auto byte_at = [&](int k) -> float {
+                        const uint32_t wd = gbytes[(k >> 2) % 6];
+                        return __uint_as_float(__byte_perm(wd, 0x4b000000u, 0x7540 | (k & 3))) - 8388608.0f;
+                    };
+                    I0 = byte_at(3 * o2); I1 = byte_at(3 * o2 + 1); I2 = byte_at(3 * o2 + 2);
+                } else {
+                    const uint8_t* gp = guide + (base + o2) * 3;
+                    I0 = (float)__ldg(gp); I1 = (float)__ldg(gp + 1); I2 = (float)__ldg(gp + 2);
+                }
+                const float q = (acc.x * fmaf(I0, k255, -0.5f) + acc.y * fmaf(I1, k255, -0.5f) + acc.z * fmaf(I2, k255, -0.5f) + acc.w) * inv_n;
+                const float qc = fminf(fmaxf(q, 0.0f), 1.0f);
+                const uint32_t u = (uint32_t)floorf(qc * 65535.0f + 0.5f);
+                if (vec) packed[(o2 >> 1) & 3] |= u << ((o2 & 1) * 16);
+                else out[base + o2] = (uint16_t)u;
+                if (qout) qout[base + o2] = q;
+            }
+            if (vec) *reinterpret_cast<uint4*>(out + base) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int SNT = 128, SR = 4, SGR = 8;
+
+template <int RT>
+int launch_guided_stream(v3d_ctx* ctx, const uint16_t* depth, int w, int h, const uint8_t* guide, int gw, int gh,
+                         int batch, int r, float eps, uint16_t* out, float* q, cudaStream_t st)
+{
+    const int win = 2 * r + 1, TW = (SNT - 2 * r) & ~7;
+    const int strips = (gw + TW - 1) / TW;
+    // segments: enough CTAs for ~3 waves of a full machine, never shorter than 64 rows
+    int segs = (3 * 148 * 4 + strips * batch - 1) / (strips * batch);
+    segs = max(1, min(segs, gh / 64));
+    int seg = (gh + segs - 1) / segs;
+    seg = (seg + SR - 1) / SR * SR;
+    segs = (gh + seg - 1) / seg;
+    const size_t sm_c = (size_t)4 * SR * (SNT + SNT / SGR + 1) * 16 + (size_t)win * SNT * 8;
+    const size_t sm_a = (size_t)SR * (SNT + SNT / SGR + 1) * 16 + (size_t)win * SNT * 16;
+    if (!(ctx->guided_attr_set & (0x100 << RT))) {
+        V3D_CUDA(cudaFuncSetAttribute(k_guided_coeff_s<RT, SNT, SR, SGR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((size_t)4 * SR * (SNT + SNT / SGR + 1) * 16 + (size_t)(2 * GRMAX + 1) * SNT * 8)));
+        V3D_CUDA(cudaFuncSetAttribute(k_guided_apply_s<RT, SNT, SR, SGR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((size_t)SR * (SNT + SNT / SGR + 1) * 16 + (size_t)(2 * GRMAX + 1) * SNT * 16)));
+        ctx->guided_attr_set |= (0x100 << RT);
+    }
+    const int vec_ok = (gw % 8 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)guide % 8 == 0);
+    dim3 grid(strips, segs, batch);
+    k_guided_coeff_s<RT, SNT, SR, SGR><<<grid, SNT, sm_c, st>>>(depth, w, h, guide, gw, gh, r, eps, seg, ctx->ab);
+    k_guided_apply_s<RT, SNT, SR, SGR><<<grid, SNT, sm_a, st>>>(ctx->ab, guide, gw, gh, r, seg, vec_ok, out, q);
+    V3D_LAUNCHED(ctx, 2);
+    return V3D_OK;
+}
+
 constexpr size_t sm_coeff_max()
 {
     return (size_t)(GT + 2 * GRMAX) * (GT + 2 * GRMAX + 1) * 8 + (size_t)13 * (GT + 2 * GRMAX) * (GT + 1) * 4;
@@ -305,6 +657,14 @@ int v3d_launch_guided(v3d_ctx* ctx, const uint16_t* depth, int w, int h, const u
         ctx->ab_bytes = need; ctx->bytes += need;
     }
     V3dScope scope(ctx, ST_GUIDED, st);
+    static const bool use_tiles = getenv("V3D_GUIDED_TILES") != nullptr;     // development A/B switch
+    if (!use_tiles) {
+        switch (r) {
+            case 8: return launch_guided_stream<8>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);
+            case 4: return launch_guided_stream<4>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);
+            default: return launch_guided_stream<0>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);
+        }
+    }
     switch (r) {
         case 8: return launch_guided_rt<8>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);
         case 4: return launch_guided_rt<4>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);
