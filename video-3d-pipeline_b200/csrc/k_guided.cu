@@ -44,7 +44,7 @@ __device__ __forceinline__ void axis_tap(int X, int w, int gw, int& i0, int& i1,
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 __device__ __forceinline__ void sub4(float4& a, const float4& b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; a.w -= b.w; }
 
-struct RowTap { int gy, y0, y1; float fy; };
+struct RowTap { int gy, o0, o1; float fy; };   // guide row; element offsets of the two depth rows; weight
 
 // byte k of `w` as 8388608 + byte (one PRMT); subtract (8388608 + centre) to get the centred value exactly
 template <int K> __device__ __forceinline__ float byte_magic(uint32_t w)
@@ -58,11 +58,22 @@ __device__ __forceinline__ void kahan(float& v, float& c, float d)
     v = t;
 }
 
+// Pitch (slots) of one row of column sums: column x sits at x + x/GR, so a warp whose lanes take consecutive runs
+// reads consecutive slots mod 8; making the pitch congruent to the number of runs keeps that true across rows.
+template <int RT, int NT, int GR>
+__host__ __device__ constexpr int row_pitch()
+{
+    const int runs = ((NT - 2 * (RT > 0 ? RT : GRMAX)) & ~7) / GR;
+    int vp = NT + NT / GR + 1;
+    while ((vp - runs) % 8 != 0) vp++;
+    return vp;
+}
+
 // shared-memory bytes of k_guided_coeff_s
-template <int NT, int R, int GR>
+template <int RT, int NT, int R, int GR>
 constexpr size_t coeff_s_smem(int win)
 {
-    return (size_t)3 * R * (NT + NT / GR + 1) * 16 + (size_t)R * (NT + NT / GR + 1) * 4 + (size_t)win * NT * 8 +
+    return (size_t)3 * R * row_pitch<RT, NT, GR>() * 16 + (size_t)R * row_pitch<RT, NT, GR>() * 4 + (size_t)win * NT * 8 +
            (size_t)2 * R * (NT * 3 + 16);
 }
 
@@ -74,7 +85,7 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
     extern __shared__ float4 gsm[];
     const int r = RT > 0 ? RT : r_arg, win = 2 * r + 1;
     const int TW = (NT - 2 * r) & ~7;
-    constexpr int VP = NT + NT / GR + 1;                            // slots per (plane group, row): column x at x + x/GR
+    constexpr int VP = row_pitch<RT, NT, GR>();                     // slots per (plane group, row): column x at x + x/GR
     constexpr int GSB = NT * 3 + 16;                                // staged guide row: NT pixels of rgb (+ pad), bytes
     float4* vbuf = gsm;                                             // [3 plane groups][R][VP] float4 (sums 0..11)
     float* v12 = reinterpret_cast<float*>(gsm + 3 * R * VP);        // [R][VP] float (sum 12)
@@ -99,17 +110,20 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
     float fx;
     axis_tap(gx, w, gw, x0, x1, fx);
     const float ax0 = (1.0f - fx) * s16, ax1 = fx * s16;
+    const uint16_t* const dx0 = depth + x0;
+    const uint16_t* const dx1 = depth + x1;
     auto depth_at = [&](const RowTap& rt) -> float {                // bilinear depth tap, branch free
-        const uint16_t* r0 = depth + (size_t)rt.y0 * w;
-        const uint16_t* r1 = depth + (size_t)rt.y1 * w;
-        const float top = (float)__ldg(r0 + x0) * ax0 + (float)__ldg(r0 + x1) * ax1;
-        const float bot = (float)__ldg(r1 + x0) * ax0 + (float)__ldg(r1 + x1) * ax1;
+        const float top = (float)__ldg(dx0 + rt.o0) * ax0 + (float)__ldg(dx1 + rt.o0) * ax1;
+        const float bot = (float)__ldg(dx0 + rt.o1) * ax0 + (float)__ldg(dx1 + rt.o1) * ax1;
         return top * (1.0f - rt.fy) + bot * rt.fy;
     };
     auto make_tap = [&](int j) -> RowTap {
         RowTap t;
+        int y0, y1;
         t.gy = reflect_idx(Y0 - r + j, gh);
-        axis_tap(t.gy, h, gh, t.y0, t.y1, t.fy);
+        axis_tap(t.gy, h, gh, y0, y1, t.fy);
+        t.o0 = y0 * w;
+        t.o1 = y1 * w;
         return t;
     };
     auto stage_rows = [&](int grp) {                                // guide rows of group `grp` -> gst[grp & 1]
@@ -126,8 +140,11 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
     if (tid < R) taps[0][tid] = make_tap(tid);
     if (tid == NT / 2) {                                            // strip centre: column X0 + TW/2, middle row
         RowTap c;
+        int y0, y1;
         c.gy = min(Y0 + seg_h / 2, gh - 1);
-        axis_tap(c.gy, h, gh, c.y0, c.y1, c.fy);
+        axis_tap(c.gy, h, gh, y0, y1, c.fy);
+        c.o0 = y0 * w;
+        c.o1 = y1 * w;
         const uint8_t* gp = guide + ((size_t)c.gy * gw + gx) * 3;
         centre_rgb = (uint32_t)__ldg(gp) | ((uint32_t)__ldg(gp + 1) << 8) | ((uint32_t)__ldg(gp + 2) << 16);
         centre_p = depth_at(c);
@@ -303,7 +320,7 @@ k_guided_apply_s(const float4* __restrict__ ab, const uint8_t* __restrict__ guid
     extern __shared__ float4 gsm[];
     const int r = RT > 0 ? RT : r_arg, win = 2 * r + 1;
     const int TW = (NT - 2 * r) & ~7;
-    constexpr int VP = NT + NT / GR + 1;
+    constexpr int VP = row_pitch<RT, NT, GR>();
     const int RING = win + R;            // rows of (a, b) kept: the window plus the group being prefetched
     float4* vbuf = gsm;                  // [R][VP] column sums of the group
     float4* ring = gsm + R * VP;         // [RING][NT], row j at slot j % RING, filled by cp.async
@@ -332,6 +349,7 @@ k_guided_apply_s(const float4* __restrict__ ab, const uint8_t* __restrict__ guid
         fslot = fslot + R >= RING ? fslot + R - RING : fslot + R;
     };
     if (tid < R) rows[0][tid] = reflect_idx(Y0 - r + tid, gh);
+    for (int k = R; k < RING; k++) ring[k * NT + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     fetch_rows(0);
     float4 V = make_float4(0.f, 0.f, 0.f, 0.f), C = V;
@@ -347,8 +365,7 @@ k_guided_apply_s(const float4* __restrict__ ab, const uint8_t* __restrict__ guid
             const int j = g * R + jj;
             if (j >= nrows) break;
             const float4 nv = ring[nslot * NT + tid];
-            float4 old = ring[oslot * NT + tid];
-            if (j < win) old = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 old = ring[oslot * NT + tid];              // zero while j < win (slots R.. start zeroed)
             nslot = nslot + 1 == RING ? 0 : nslot + 1;
             oslot = oslot + 1 == RING ? 0 : oslot + 1;
             kahan(V.x, C.x, nv.x - old.x); kahan(V.y, C.y, nv.y - old.y);
@@ -426,13 +443,13 @@ int launch_guided_stream(v3d_ctx* ctx, const uint16_t* depth, int w, int h, cons
     int seg = (gh + segs - 1) / segs;
     seg = (seg + SR - 1) / SR * SR;
     segs = (gh + seg - 1) / seg;
-    const size_t sm_c = coeff_s_smem<SNT, SR, SGR>(win);
+    const size_t sm_c = coeff_s_smem<RT, SNT, SR, SGR>(win);
     constexpr int SRA = 8;            // rows per group of the apply kernel
-    const size_t sm_a = (size_t)SRA * (SNT + SNT / SGR + 1) * 16 + (size_t)(win + SRA) * SNT * 16;
-    const size_t sm_a_max = (size_t)SRA * (SNT + SNT / SGR + 1) * 16 + (size_t)(2 * GRMAX + 1 + SRA) * SNT * 16;
+    const size_t sm_a = (size_t)SRA * row_pitch<RT, SNT, SGR>() * 16 + (size_t)(win + SRA) * SNT * 16;
+    const size_t sm_a_max = (size_t)SRA * row_pitch<RT, SNT, SGR>() * 16 + (size_t)(2 * GRMAX + 1 + SRA) * SNT * 16;
     if (!(ctx->guided_attr_set & (1 << RT))) {
         V3D_CUDA(cudaFuncSetAttribute(k_guided_coeff_s<RT, SNT, SR, SGR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)coeff_s_smem<SNT, SR, SGR>(2 * GRMAX + 1)));
+                                      (int)coeff_s_smem<RT, SNT, SR, SGR>(2 * GRMAX + 1)));
         V3D_CUDA(cudaFuncSetAttribute(k_guided_apply_s<RT, SNT, SRA, SGR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a_max));
         V3D_CUDA(cudaFuncSetAttribute(k_guided_apply_s<RT, SNT, SRA, SGR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a_max));
         ctx->guided_attr_set |= (1 << RT);
