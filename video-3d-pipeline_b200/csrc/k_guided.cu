@@ -78,7 +78,7 @@ constexpr size_t coeff_s_smem(int win)
 }
 
 template <int RT, int NT, int R, int GR>
-__global__ void __launch_bounds__(NT, 512 / NT)
+__global__ void __launch_bounds__(NT, (R >= 8 ? 256 : 512) / NT)
 k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t* __restrict__ guide, int gw, int gh,
                  int r_arg, float eps, int seg, float4* __restrict__ ab)
 {
