@@ -12,6 +12,7 @@
 //   step:                 L[d] = C[d] + min(M[d], min(M[d-1], M[d+1]) + P1)
 // A predecessor outside the window contributes L = 0, i.e. M = 0, which is also the initial state.
 #include "path_common.cuh"
+#include "tma.cuh"
 
 #include <cooperative_groups.h>
 #include <type_traits>
@@ -94,8 +95,9 @@ k_path_vert(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, 
 // S is written once per sweep instead of three reads of C and a write + two read-modify-writes of S.
 // Path state M lives in shared memory ([dir][column][d]); a diagonal path moves to the neighbouring
 // column every row, so the only inter-warp traffic is one 2*NR*64-byte state vector per warp
-// boundary and direction per row, exchanged through (distributed) shared memory behind one cluster
-// barrier per row.
+// boundary and direction per row.  Each warp PUSHES its two boundary vectors into its neighbours' inboxes
+// (st.async through distributed shared memory, completion counted on the receiver's mbarrier), so a warp
+// synchronises with its two neighbours only: no cluster-wide barrier, no memory fence, no remote loads.
 // ------------------------------------------------------------------------------------------
 // V3_CL CTAs per cluster, V3_NW warps per CTA: 8 x 32 for D <= 128 (portable cluster size); 16 x 16 for
 // D = 256, whose 512-byte state vectors need the shared memory of 16 SMs per frame (non-portable size).
@@ -109,7 +111,8 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     extern __shared__ uint4 v3smem[];
     constexpr int COLS = V3_NW * CPW;
     VT* Mst = reinterpret_cast<VT*>(v3smem);          // [3][COLS][32]   path state
-    VT* xch = Mst + 3 * COLS * 32;                    // [2][V3_NW][2][32] boundary exchange, double buffered
+    VT* inbox = Mst + 3 * COLS * 32;                  // [2][V3_NW][2][32] boundary vectors from the neighbours, double buffered
+    uint64_t* mb = reinterpret_cast<uint64_t*>(inbox + 2 * V3_NW * 2 * 32);   // [2][V3_NW] one mbarrier per warp and buffer
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int frame = blockIdx.x / V3_CL;
@@ -127,16 +130,11 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     for (int d = 0; d < 3; d++)
 #pragma unroll
         for (int j = 0; j < CPW; j++) Mst[((d * COLS) + lc0 + j) * 32 + lane] = zero;
+    if (threadIdx.x < 2 * V3_NW) mbar_init(mb + threadIdx.x, 1);
+    fence_mbar_init_cluster();
+    cluster.sync();
 
-    // where the neighbours publish: slot 0 = last column's (x-1)-direction state, slot 1 = first column's (x+1) one
-    const VT* left_x = nullptr;
-    const VT* right_x = nullptr;
-    if (w > 0) left_x = xch + ((w - 1) * 2 + 0) * 32 + lane;
-    else if (rank > 0) left_x = cluster.map_shared_rank(xch, rank - 1) + ((V3_NW - 1) * 2 + 0) * 32 + lane;
-    if (w < V3_NW - 1) right_x = xch + ((w + 1) * 2 + 1) * 32 + lane;
-    else if (rank < V3_CL - 1) right_x = cluster.map_shared_rank(xch, rank + 1) + (0 * 2 + 1) * 32 + lane;
-    constexpr int PARSTRIDE = V3_NW * 2 * 32;
-
+    constexpr int PARSTRIDE = V3_NW * 2 * 32;         // inbox elements per buffer
     const int nv = min(max(W1 - gcol0, 0), CPW);      // columns of this warp inside the window
     const bool has_right = gcol0 + CPW < W1;          // a column to the right of this warp's last one exists
     VT cq[CPW], sq[CPW];
@@ -154,7 +152,24 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     VT* Md = Mst + (0 * COLS + lc0) * 32 + lane;      // this warp's state rows, one per direction
     VT* Ml = Mst + (1 * COLS + lc0) * 32 + lane;
     VT* Mr = Mst + (2 * COLS + lc0) * 32 + lane;
-    VT* xo = xch + (w * 2) * 32 + lane;
+    // inbox slot 0 receives the left neighbour's (x-1)-direction state of its last column, slot 1 the right
+    // neighbour's (x+1)-direction state of its first column
+    const bool has_left = gcol0 > 0 && nv > 0;
+    const VT* in_l = inbox + (w * 2 + 0) * 32 + lane;
+    const VT* in_r = inbox + (w * 2 + 1) * 32 + lane;
+    uint64_t* my_bar = mb + w;
+    const uint32_t rx_bytes = ((has_left ? 1u : 0u) + (has_right ? 1u : 0u)) * 32u * (uint32_t)sizeof(VT);
+    uint32_t to_l = 0, to_l_bar = 0, to_r = 0, to_r_bar = 0;      // cluster addresses in the neighbours' shared memory
+    if (has_left) {
+        const int nr = w > 0 ? rank : rank - 1, nw = w > 0 ? w - 1 : V3_NW - 1;
+        to_l = mapa_u32(smem_u32(inbox + (nw * 2 + 1) * 32 + lane), nr);
+        to_l_bar = mapa_u32(smem_u32(mb + nw), nr);
+    }
+    if (has_right) {
+        const int nr = w < V3_NW - 1 ? rank : rank + 1, nw = w < V3_NW - 1 ? w + 1 : 0;
+        to_r = mapa_u32(smem_u32(inbox + (nw * 2 + 0) * 32 + lane), nr);
+        to_r_bar = mapa_u32(smem_u32(mb + nw), nr);
+    }
     // One column: the three path steps, the state write-back and the S store.  inl / inr are the previous
     // row's states arriving from the left / right neighbour column.
     auto do_col = [&](int j, const uint32_t (&inl)[NR], const uint32_t (&inr)[NR], bool more, const VT* Cnext,
@@ -190,9 +205,10 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         const VT* Cnext = C + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
         VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
         const VT* Snext = S + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
-        xo[par * PARSTRIDE] = Ml[(CPW - 1) * 32];
-        xo[par * PARSTRIDE + 32] = Mr[0];
-        cluster.barrier_arrive();
+        const uint32_t phase = (i >> 1) & 1;
+        if (has_right) st_async(to_r + par * PARSTRIDE * (uint32_t)sizeof(VT), Ml[(CPW - 1) * 32], to_r_bar + par * V3_NW * 8);
+        if (has_left) st_async(to_l + par * PARSTRIDE * (uint32_t)sizeof(VT), Mr[0], to_l_bar + par * V3_NW * 8);
+        if (lane == 0 && rx_bytes) mbar_expect_tx(my_bar + par * V3_NW, rx_bytes);
         if (nv == CPW && CPW >= 3) {
             // Full warp: the interior columns need nothing from other warps, so they run between the
             // barrier's arrive and wait; only the two edge columns wait for the neighbours' states.
@@ -208,24 +224,24 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
 #pragma unroll
                 for (int r = 0; r < NR; r++) carry[r] = nextcarry[r];
             }
-            cluster.barrier_wait();
+            if (rx_bytes) mbar_wait(my_bar + par * V3_NW, phase);
             uint32_t edge[NR];
-            if (gcol0 > 0) unpack<NR>(left_x[par * PARSTRIDE], edge);
+            if (gcol0 > 0) unpack<NR>(in_l[par * PARSTRIDE], edge);
             else {
 #pragma unroll
                 for (int r = 0; r < NR; r++) edge[r] = 0;
             }
             do_col(0, edge, save_r1, more, Cnext, Snext, Srow);
-            if (has_right) unpack<NR>(right_x[par * PARSTRIDE], edge);
+            if (has_right) unpack<NR>(in_r[par * PARSTRIDE], edge);
             else {
 #pragma unroll
                 for (int r = 0; r < NR; r++) edge[r] = 0;
             }
             do_col(CPW - 1, carry, edge, more, Cnext, Snext, Srow);
         } else {
-            cluster.barrier_wait();
+            if (rx_bytes) mbar_wait(my_bar + par * V3_NW, phase);
             uint32_t carry[NR], inr[NR];
-            if (gcol0 > 0 && nv > 0) unpack<NR>(left_x[par * PARSTRIDE], carry);
+            if (has_left) unpack<NR>(in_l[par * PARSTRIDE], carry);
             else {
 #pragma unroll
                 for (int r = 0; r < NR; r++) carry[r] = 0;
@@ -242,7 +258,7 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
                             for (int r = 0; r < NR; r++) inr[r] = 0;
                         }
                     } else if (has_right) {
-                        unpack<NR>(right_x[par * PARSTRIDE], inr);
+                        unpack<NR>(in_r[par * PARSTRIDE], inr);
                     } else {
 #pragma unroll
                         for (int r = 0; r < NR; r++) inr[r] = 0;
@@ -262,7 +278,7 @@ template <int NR, int CPW, int V3_CL, int V3_NW>
 int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
 {
     using VT = typename Vec<NR>::T;
-    const size_t smem = ((size_t)3 * V3_NW * CPW * 32 + (size_t)2 * V3_NW * 2 * 32) * sizeof(VT);
+    const size_t smem = ((size_t)3 * V3_NW * CPW * 32 + (size_t)2 * V3_NW * 2 * 32) * sizeof(VT) + (size_t)2 * V3_NW * 8;
     auto kw = k_path_vert3<NR, CPW, S_WRITE, V3_CL, V3_NW>;
     auto ka = k_path_vert3<NR, CPW, S_ACCUM, V3_CL, V3_NW>;
     V3D_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

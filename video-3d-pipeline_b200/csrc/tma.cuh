@@ -46,4 +46,28 @@ template <int N> __device__ __forceinline__ void bulk_wait_read()
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- DSMEM push: store into another CTA's shared memory, completion counted on that CTA's mbarrier ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_async(uint32_t dst_cluster, const uint32_t& v, uint32_t bar_cluster)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster),
+                 "r"(v), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_async(uint32_t dst_cluster, const uint2& v, uint32_t bar_cluster)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dst_cluster),
+                 "r"(v.x), "r"(v.y), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_async(uint32_t dst_cluster, const uint4& v, uint32_t bar_cluster)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     dst_cluster), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
 }  // namespace
