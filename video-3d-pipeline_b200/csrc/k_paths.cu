@@ -177,10 +177,10 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         uint32_t Cr[NR], Sr[NR], L[NR], M[NR];
         unpack<NR>(cq[j], Cr);
         if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
-        if (more) {
-            cq[j] = __ldg(Cnext + j * 32);
-            if (SMODE == S_ACCUM) sq[j] = Snext[j * 32];
-        }
+        // next row's operands (on the last row Cnext / Snext point at the current row again: an unconditional
+        // load goes straight into cq / sq, a predicated one costs a dependent move that waits for it)
+        cq[j] = __ldg(Cnext + j * 32);
+        if (SMODE == S_ACCUM) sq[j] = Snext[j * 32];
         unpack<NR>(Md[j * 32], M);                               // (x, y-sy)
         path_step<NR>(M, Cr, L, P1p, P2p, lane);
         Md[j * 32] = pack<NR>(M);
