@@ -5,6 +5,7 @@
 The .so lands next to the Python package (video_3d_pipeline/libv3d.so) so that it
 travels with the source tree; it is git-ignored.
 """
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -30,7 +31,8 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("V3D_NVCC_EXTRA", "").split()      # e.g. -DV3D_COST_RPB=5 for tuning experiments
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", str(OUT)] + [str(CSRC / s) for s in SOURCES]
     print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

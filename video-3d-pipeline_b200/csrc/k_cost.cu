@@ -100,7 +100,8 @@ k_prefilter_expand(const uint8_t* __restrict__ left, const uint8_t* __restrict__
 // Cost volume.  Block = a strip of TXW window columns (one warp per column) sweeping a band of rows.
 //   lane l owns the disparity pairs d = 2l + 64k (+1), k < NR        (D = 64*NR)
 //   vertical (2R+1)-row sum: sliding window in registers (ring of 2R+1 packed pix values)
-//   horizontal (2R+1)-column sum: through shared memory, clamped in WINDOW coordinates
+//   horizontal (2R+1)-column sum: through shared memory, clamped in WINDOW coordinates; a warp then owns a
+//   run of 4 output columns of one row and slides the window over the 4 + 2R column sums it loaded once
 // ---------------------------------------------------------------------------------------------
 // The row loop is unrolled by U = max(K, 3) rows and the kernel keeps U staged rows and U vertical-sum
 // buffers, so that the ring slot (ph % K), the staging buffer and the vbuf slot of a row are all
@@ -147,8 +148,6 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;
     const int b = blockIdx.z;
     const int xs = blockIdx.x * TX;
-    const int x = xs - R + c;                       // window column of this warp
-    const bool inner = (c >= R && c < TXW - R && x < W1);
     const int y0 = blockIdx.y * band_h, y1 = min(H, y0 + band_h);
     const int ystart = y0 - R;
     const int nrows = (y1 + R - ystart + U - 1) / U * U;    // padded to whole unrolled groups
@@ -204,12 +203,18 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     constexpr int LSTG = TXW * 2;
     uint32_t* v_p = &sm.vbuf[0][c][lane];
     constexpr int VSTG = TXW * (D / 2);
-    const uint32_t* vb = &sm.vbuf[0][0][lane];
-    int nb_off[K];
-#pragma unroll
-    for (int dx = -R; dx <= R; dx++) nb_off[dx + R] = (min(max(x + dx, 0), W1 - 1) - (xs - R)) * (D / 2);
-    uint32_t* out = C + (((ptrdiff_t)b * H + (ystart - R)) * W1 + x) * (D / 2) + lane;   // output row of sweep row ystart
+    // Horizontal sum: warp c owns one (row of the group, run of HN output columns, register k) item.  The
+    // HN + 2R columns a run touches are loaded once and the window slides in registers.
+    constexpr int HN = 4, NRUN = (TX + HN - 1) / HN, NITEM = RPB * NRUN * NR;
+    static_assert(NITEM <= TXW, "one horizontal item per warp");
+    const int h_s = c / (NRUN * NR), h_run = (c % (NRUN * NR)) / NR, h_k = c % NR;
+    const int h_x = xs + h_run * HN;                               // first output column (window coordinates)
+    const int h_n = min(HN, min(xs + TX, W1) - h_x);               // output columns of this item (<= 0: none)
+    const bool h_flat = xs - R >= 0 && xs - R + TXW <= W1;         // no clamping anywhere in this strip
+    const uint32_t* h_vb = &sm.vbuf[0][0][32 * h_k + lane];
+    uint32_t* h_out = C + (((ptrdiff_t)b * H + (ystart - R)) * W1 + h_x) * (D / 2) + 32 * h_k + lane;
     const size_t out_row = (size_t)W1 * (D / 2);
+    const bool h_real = !PAD || 2 * (lane + 32 * h_k) < Dreal;     // padded disparities get a cost no real one can reach
 
     uint32_t parity = 0;
     for (int row = ystart; row < yend; row += U, parity ^= 1) {
@@ -242,27 +247,43 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
                 }
             }
             __syncthreads();        // vbuf slots complete; every thread is done with the previous group's stages
+            if (tid == 0) {
 #pragma unroll
-            for (int s = 0; s < RPB; s++) {
-                const int ph = pg + s;
-                const int r = row + ph;
-                // refill the stage a row of the PREVIOUS group used (U - RPB rows ahead of this one)
-                if (tid == 0 && r + U - RPB < yend) issue(r + U - RPB, (ph + U - RPB) % U);
-                const int yo = r - R;
-                if (inner && yo >= y0 && yo < y1) {
+                for (int s = 0; s < RPB; s++) {
+                    // refill the stage a row of the PREVIOUS group used (U - RPB rows ahead of this one)
+                    const int r = row + pg + s;
+                    if (r + U - RPB < yend) issue(r + U - RPB, (pg + s + U - RPB) % U);
+                }
+            }
+            if (c < NITEM && h_n > 0) {
+                const int ph = pg + h_s;                    // (h_s is warp-uniform, so is everything below)
+                const int yo = row + ph - R;
+                if (yo >= y0 && yo < y1) {
+                    const uint32_t* vb = h_vb + ph * VSTG;
+                    uint32_t v[HN + 2 * R];
+                    if (h_flat && h_n == HN) {
 #pragma unroll
-                    for (int k = 0; k < NR; k++) {
-                        uint32_t acc = 0;
+                        for (int i = 0; i < HN + 2 * R; i++) v[i] = vb[(h_run * HN + i) * (D / 2)];
+                    } else {                                // strip on the window border, or a short last run
 #pragma unroll
-                        for (int dx = 0; dx < K; dx++) acc += vb[ph * VSTG + nb_off[dx] + 32 * k];
-                        // padded disparities get a cost no real one can reach: they never win a minimum and
-                        // their path state saturates at P2, i.e. they act like the missing neighbour d = D
-                        out[32 * k] = (!PAD || 2 * (lane + 32 * k) < Dreal) ? acc : 0x20002000u;
+                        for (int i = 0; i < HN + 2 * R; i++)
+                            v[i] = i < h_n + 2 * R ? vb[(min(max(h_x - R + i, 0), W1 - 1) - (xs - R)) * (D / 2)] : 0u;
+                    }
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int i = 0; i <= 2 * R; i++) acc += v[i];
+                    uint32_t* o = h_out + (size_t)ph * out_row;
+#pragma unroll
+                    for (int j = 0; j < HN; j++) {
+                        if (j > 0) acc += v[j + 2 * R] - v[j - 1];          // halves never borrow: acc includes v[j-1]
+                        // padded disparities: they never win a minimum and their path state saturates at P2,
+                        // i.e. they act like the missing neighbour d = D
+                        if (j < h_n) o[j * (D / 2)] = h_real ? acc : 0x20002000u;
                     }
                 }
-                out += out_row;
             }
         }
+        h_out += (size_t)U * out_row;
     }
 }
 
