@@ -55,7 +55,7 @@ NCU_DRAM_BYTES_PER_FRAME = {      # profiles/r01_final_ncu_full_top6.csv
     "vertical": (7.433441e9 + 7.386856e9) / 15,
     "lr": (14.864263e9 + 7.392594e9) / 15,
     "wta": (14.863643e9 + 0.237814e9) / 15,
-    "guided": (0.435557e9 + 1.934585e9 + 2.363982e9 + 0.245625e9) / 2 / 15,
+    "guided": (0.452210e9 + 1.938373e9 + 2.407520e9 + 0.244936e9) / 2 / 15,
 }
 
 
@@ -353,7 +353,7 @@ def run_ours(args):
             "vertical": ("k_path_vert3", 1, 2 * vol),
             "lr": ("k_path_lr_tma", 1, 3 * vol),
             "wta": ("k_path_rl_wta_tma", 1, 2 * vol),
-            "guided": ("k_guided_coeff + k_guided_apply (avg of 2)", 2, (GUIDE_BYTES + 16 * GW * GH) / 2 + GW * GH * 9.0),
+            "guided": ("k_guided_coeff_s + k_guided_apply_s (avg of 2)", 2, (GUIDE_BYTES + 16 * GW * GH) / 2 + GW * GH * 9.0),
         }
         dom_name = max(kernels, key=lambda k: stages.get(k, 0.0) / kernels[k][1])
         kname, nl, design_pf = kernels[dom_name]
@@ -420,7 +420,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0,
                     help="frames per step per GPU (default: lanes x the co-resident clusters of the fused sweep, 45 on most B200s)")
-    ap.add_argument("--lanes", type=int, default=3, help="streams/contexts the batch is split over")
+    ap.add_argument("--lanes", type=int, default=5, help="streams/contexts the batch is split over")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

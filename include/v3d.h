@@ -165,6 +165,15 @@ int v3d_depth_frames_host(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, 
 int v3d_fused_sweep_clusters(const v3d_ctx* ctx);
 /* Number of kernel launches issued through this context so far. */
 unsigned long long v3d_launch_count(const v3d_ctx* ctx);
+/* OPT-IN behaviour change (the default reproduces the reference).
+ * save_depth_map (depth.py:400-401) stretches every frame to its own min/max, so
+ * the 16-bit depth scale flickers from frame to frame.  With fixed = 1 the uint16
+ * maps of subsequent v3d_postprocess / v3d_depth_frames* calls use one scale for
+ * the whole clip instead:  u16 = trunc(clip((d - lo) / (hi - lo), 0, 1) * 65535)
+ * in fp32 with d in pixels.  fixed = 0 restores the per-frame min-max.
+ * Returns V3D_EINVAL unless hi > lo. */
+int v3d_set_depth_scale(v3d_ctx* ctx, int fixed, float lo, float hi);
+
 /* Record per-stage CUDA-event timings for subsequent calls (0 = off).  With
  * timing on, v3d_stage_ms(ctx, i, &name) returns the accumulated milliseconds
  * of stage i (synchronises) or a negative value when i is out of range. */

@@ -125,6 +125,8 @@ def test_cache_key_is_the_references(tmp_path):
     for i in range(2):
         (p / f"depth_{i:06d}.png").write_bytes(b"x")
     assert ex.is_cached(p, 2) and not ex.is_cached(p, 3)
+    ex.depth_scale, ex.num_disparities = "fixed", 64     # opt-in output format gets its own cache entry
+    assert ex.get_cache_path("clip.mkv", 5, 100) != p
 
 
 def test_video_info_fallback_and_work_dir(tmp_path):

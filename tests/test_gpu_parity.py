@@ -204,6 +204,55 @@ def test_guided_upscale_full_4k():
     assert np.abs(out.astype(np.int64) - ou.astype(np.int64)).max() <= 1
 
 
+@pytest.mark.parametrize("gw,gh", [(960, 540), (958, 541), (452, 300)])
+def test_guided_vector_and_scalar_store_paths_agree(gw, gh):
+    """Without the float tap the apply kernel packs 8 outputs into one 16-byte store and reads their guide
+    bytes as 3 x 8 bytes (taken when gw % 8 == 0 and the pointers are aligned); with the tap, or for other
+    widths / a misaligned guide, it stores pixel by pixel.  All of them must give the same uint16 image, and
+    interior strips (cp.async-staged guide rows) must match border strips (byte loads)."""
+    w, h = 480, 270
+    d = synthetic.depth_u16(8, 0, w, h)
+    g = synthetic.guide_frame(8, 0, gw, gh)
+    dt = torch.from_numpy(d.view(np.int16))[None].cuda().view(torch.uint16)
+    with nv.Context(80, 8, nv.SgbmParams()) as ctx:
+        fast = _u16(ctx.guided_upscale(dt, torch.from_numpy(g)[None].cuda(), 8, 1e-3))[0]
+        slow, q = ctx.guided_upscale(dt, torch.from_numpy(g)[None].cuda(), 8, 1e-3, want_q=True)
+        slow = _u16(slow)[0]
+        # same guide at an address that is only 1-byte aligned
+        buf = torch.empty(g.size + 1, dtype=torch.uint8, device="cuda")
+        shifted = buf[1:].view(1, gh, gw, 3)
+        shifted.copy_(torch.from_numpy(g)[None])
+        mis = _u16(ctx.guided_upscale(dt, shifted, 8, 1e-3))[0]
+    assert np.array_equal(fast, slow) and np.array_equal(fast, mis)
+    oq, ou = og.guided_upscale(d, g, 8, 1e-3)
+    assert np.abs(q[0].cpu().numpy() - oq).max() < 0.5 / 65535
+    assert np.abs(fast.astype(np.int64) - ou.astype(np.int64)).max() <= 1
+
+
+def test_fixed_depth_scale_is_opt_in_and_exact():
+    """v3d_set_depth_scale(fixed) replaces the per-frame min-max by one clip-level scale; the
+    default stays the reference's.  Checked against the same three fp32 operations in numpy."""
+    W, H, D, B = 320, 96, 64, 2
+    frames = np.stack([synthetic.sbs_frame(9, t, W, H, D) for t in range(B)])
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D), max_batch=B) as ctx:
+        ref = ctx.depth_frames(torch.from_numpy(frames).cuda(), False, want=("f32", "u16"))
+        ref_u16, f32 = _u16(ref["u16"]), ref["f32"].cpu().numpy()
+        ctx.set_depth_scale(True, 0.0, float(D))
+        fix = _u16(ctx.depth_frames(torch.from_numpy(frames).cuda(), False, want=("u16",))["u16"])
+        fix_n = _u16(ctx.normalize_u16(torch.from_numpy(f32).cuda()))
+        with pytest.raises(ValueError):
+            ctx.set_depth_scale(True, 4.0, 4.0)
+        ctx.set_depth_scale(False)
+        again = _u16(ctx.depth_frames(torch.from_numpy(frames).cuda(), False, want=("u16",))["u16"])
+    for b in range(B):
+        assert np.array_equal(ref_u16[b], cv2_chain.normalize_u16(f32[b]))          # default = reference
+    t = (f32 - np.float32(0.0)) / (np.float32(D) - np.float32(0.0))
+    want = (np.clip(t, np.float32(0), np.float32(1)) * np.float32(65535.0)).astype(np.uint16)
+    assert np.array_equal(fix, want) and np.array_equal(fix_n, want)
+    assert np.array_equal(again, ref_u16)
+    assert not np.array_equal(fix, ref_u16)
+
+
 def test_host_entry_point_matches_device_path():
     W, H, D, B = 320, 120, 64, 3
     frames = np.stack([synthetic.sbs_frame(6, t, W, H, D) for t in range(B)])

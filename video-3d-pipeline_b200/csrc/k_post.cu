@@ -262,7 +262,7 @@ k_minmax(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, in
 
 __global__ void __launch_bounds__(256)
 k_epilogue(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int W, int H,
-           const int* __restrict__ mm, float* __restrict__ f32, uint16_t* __restrict__ u16)
+           const int* __restrict__ mm, float* __restrict__ f32, uint16_t* __restrict__ u16, int fixed, float lo, float hi)
 {
     const int b = blockIdx.y;
     const int n = W * H;
@@ -272,7 +272,10 @@ k_epilogue(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, 
     const int v = max((int)disp[(size_t)b * dstride_e + (size_t)y * dpitch_e + x], 0);
     const float f = __fdiv_rn((float)v, 16.0f);
     if (f32) f32[(size_t)b * n + i] = f;
-    if (u16) {
+    if (u16 && fixed) {      // opt-in clip-level scale (v3d_set_depth_scale)
+        const float t = __fdiv_rn(__fsub_rn(f, lo), __fsub_rn(hi, lo));
+        u16[(size_t)b * n + i] = (uint16_t)__fmul_rn(fminf(fmaxf(t, 0.0f), 1.0f), 65535.0f);
+    } else if (u16) {
         const float mn = __fdiv_rn((float)mm[2 * b], 16.0f), mx = __fdiv_rn((float)mm[2 * b + 1], 16.0f);
         uint16_t o = 0;
         if (mx > mn) {
@@ -305,11 +308,17 @@ k_minmax_f32(const float* __restrict__ in, size_t n, int* __restrict__ mm)
 }
 
 __global__ void __launch_bounds__(256)
-k_normalize_f32(const float* __restrict__ in, size_t n, const int* __restrict__ mm, uint16_t* __restrict__ out)
+k_normalize_f32(const float* __restrict__ in, size_t n, const int* __restrict__ mm, uint16_t* __restrict__ out,
+                int fixed, float lo, float hi)
 {
     const int b = blockIdx.y;
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (fixed) {             // opt-in clip-level scale (v3d_set_depth_scale)
+        const float t = __fdiv_rn(__fsub_rn(in[(size_t)b * n + i], lo), __fsub_rn(hi, lo));
+        out[(size_t)b * n + i] = (uint16_t)__fmul_rn(fminf(fmaxf(t, 0.0f), 1.0f), 65535.0f);
+        return;
+    }
     const float mn = funkey(mm[2 * b]), mx = funkey(mm[2 * b + 1]);
     uint16_t o = 0;
     if (mx > mn) o = (uint16_t)__fmul_rn(__fdiv_rn(__fsub_rn(in[(size_t)b * n + i], mn), __fsub_rn(mx, mn)), 65535.0f);
@@ -321,12 +330,15 @@ k_normalize_f32(const float* __restrict__ in, size_t n, const int* __restrict__ 
 int v3d_launch_normalize_f32(v3d_ctx* ctx, const float* in, size_t n, int batch, uint16_t* out, cudaStream_t st)
 {
     V3dScope scope(ctx, ST_POST, st);
-    k_minmax_init<<<(batch + 255) / 256, 256, 0, st>>>(ctx->minmax, batch);
-    dim3 g(148 * 2, batch);
-    k_minmax_f32<<<g, 256, 0, st>>>(in, n, ctx->minmax);
+    if (!ctx->fixed_scale) {
+        k_minmax_init<<<(batch + 255) / 256, 256, 0, st>>>(ctx->minmax, batch);
+        dim3 g(148 * 2, batch);
+        k_minmax_f32<<<g, 256, 0, st>>>(in, n, ctx->minmax);
+        V3D_LAUNCHED(ctx, 2);
+    }
     dim3 grid((unsigned)((n + 255) / 256), batch);
-    k_normalize_f32<<<grid, 256, 0, st>>>(in, n, ctx->minmax, out);
-    V3D_LAUNCHED(ctx, 3);
+    k_normalize_f32<<<grid, 256, 0, st>>>(in, n, ctx->minmax, out, ctx->fixed_scale, ctx->scale_lo, ctx->scale_hi);
+    V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
 
@@ -369,14 +381,15 @@ int v3d_launch_post(v3d_ctx* ctx, const int16_t* disp, size_t dpitch, size_t dst
 {
     V3dScope scope(ctx, ST_POST, st);
     const int W = ctx->W, H = ctx->H, n = W * H;
-    if (u16) {
+    if (u16 && !ctx->fixed_scale) {
         k_minmax_init<<<(batch + 255) / 256, 256, 0, st>>>(ctx->minmax, batch);
         dim3 g(148 * 2, batch);
         k_minmax<<<g, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax);
         V3D_LAUNCHED(ctx, 2);
     }
     dim3 grid((n + 255) / 256, batch);
-    k_epilogue<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax, f32, u16);
+    k_epilogue<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax, f32, u16, ctx->fixed_scale,
+                                     ctx->scale_lo, ctx->scale_hi);
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }

@@ -188,6 +188,16 @@ int v3d_set_debug_taps(v3d_ctx* ctx, int enabled)
     return V3D_OK;
 }
 
+int v3d_set_depth_scale(v3d_ctx* ctx, int fixed, float lo, float hi)
+{
+    if (!ctx) return v3d_fail(V3D_EINVAL, "null context");
+    if (fixed && !(hi > lo)) return v3d_fail(V3D_EINVAL, "fixed depth scale needs hi > lo (got %g, %g)", lo, hi);
+    ctx->fixed_scale = fixed ? 1 : 0;
+    ctx->scale_lo = lo;
+    ctx->scale_hi = hi;
+    return V3D_OK;
+}
+
 int v3d_set_timing(v3d_ctx* ctx, int enabled)
 {
     if (!ctx) return v3d_fail(V3D_EINVAL, "null context");

@@ -47,6 +47,7 @@ struct v3d_ctx {
     int timing;
     int debug_taps;          // keep S_total and the pre-speckle median for v3d_debug_tap
     int guided_attr_set;
+    int fixed_scale; float scale_lo, scale_hi;     // v3d_set_depth_scale (0 = per-frame min-max, the reference)
     int max_clusters;        // co-resident frame clusters of the fused vertical sweep (0 = not queried)
     int no_fused_vertical;
     int h_attr_set;

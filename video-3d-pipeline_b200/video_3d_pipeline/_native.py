@@ -68,13 +68,14 @@ def lib():
     L.v3d_fused_sweep_clusters.restype = i32
     L.v3d_launch_count.argtypes = [vp]
     L.v3d_launch_count.restype = C.c_ulonglong
+    L.v3d_set_depth_scale.argtypes = [vp, i32, C.c_float, C.c_float]
     L.v3d_set_timing.argtypes = [vp, i32]
     L.v3d_reset_timing.argtypes = [vp]
     L.v3d_stage_ms.argtypes = [vp, i32, C.POINTER(C.c_char_p)]
     L.v3d_stage_ms.restype = C.c_double
     for name in ("v3d_create", "v3d_destroy", "v3d_split_gray", "v3d_bgr_to_gray", "v3d_unsqueeze_bgr",
                  "v3d_sgbm_compute", "v3d_set_debug_taps", "v3d_debug_tap", "v3d_debug_tap_copy", "v3d_postprocess", "v3d_normalize_u16",
-                 "v3d_guided_upscale", "v3d_depth_frames", "v3d_depth_frames_host", "v3d_set_timing",
+                 "v3d_guided_upscale", "v3d_depth_frames", "v3d_depth_frames_host", "v3d_set_depth_scale", "v3d_set_timing",
                  "v3d_reset_timing"):
         getattr(L, name).restype = i32
     _lib = L
@@ -166,6 +167,11 @@ class Context:
     @property
     def fused_sweep_clusters(self):
         return int(lib().v3d_fused_sweep_clusters(self._h))
+
+    def set_depth_scale(self, fixed, lo=0.0, hi=1.0):
+        """Opt-in clip-level uint16 scale: u16 = trunc(clip((d - lo) / (hi - lo), 0, 1) * 65535).
+        fixed=False restores the reference's per-frame min-max (depth.py:400-401)."""
+        _check(lib().v3d_set_depth_scale(self._h, int(bool(fixed)), C.c_float(lo), C.c_float(hi)), "v3d_set_depth_scale")
 
     def set_timing(self, on):
         _check(lib().v3d_set_timing(self._h, int(bool(on))), "v3d_set_timing")

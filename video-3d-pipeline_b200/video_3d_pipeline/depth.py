@@ -48,7 +48,8 @@ class HybridStereoDepthExtractor:
                  gpu_index: int = 0,
                  decode_threads: int = 4,
                  png_threads: int = 8,
-                 png_compression: int = 1):
+                 png_compression: int = 1,
+                 depth_scale: str = "frame"):
         # depth.py:33-40
         self.device = device
         self.work_dir = create_work_directory(work_dir)
@@ -65,6 +66,11 @@ class HybridStereoDepthExtractor:
         self.decode_threads = int(decode_threads)      # host pipeline knobs
         self.png_threads = int(png_threads)
         self.png_compression = int(png_compression)    # zlib level of the 16-bit PNGs; pixels are identical
+        # "frame": per-frame min-max like the reference (depth.py:400-401).  "fixed": opt-in clip-level scale
+        # 0..numDisparities px -> 0..65535, so the depth scale does not flicker between frames.
+        if depth_scale not in ("frame", "fixed"):
+            raise ValueError(f"depth_scale must be 'frame' or 'fixed', not {depth_scale!r}")
+        self.depth_scale = depth_scale
 
         if not str(device).startswith("cuda"):
             raise RuntimeError(f"device {device!r}: this build has no CPU path, use device='cuda'")
@@ -106,11 +112,14 @@ class HybridStereoDepthExtractor:
                 c.close()
             self._ctx = c = _native.Context(eye_w, eye_h, self.sgbm_params(),
                                             max_batch=max(batch, self.batch_size), device=self.gpu_index)
+            c.set_depth_scale(self.depth_scale == "fixed", 0.0, float(self.num_disparities))
         return c
 
     # ------------------------------------------------------------------ cache (depth.py:116-140)
     def get_cache_path(self, video_path: str, frame_start: int, frame_count: int) -> Path:
         key = f"{video_path}_{frame_start}_{frame_count}_{self.model_checkpoint}_{self.unsqueeze_sbs}"
+        if getattr(self, "depth_scale", "frame") != "frame":      # the reference key (depth.py:118) stays as is for reference behaviour
+            key += f"_{self.depth_scale}{self.num_disparities}"
         sub = self.cache_dir / f"depth_{hashlib.md5(key.encode()).hexdigest()[:16]}"
         sub.mkdir(exist_ok=True)
         return sub
@@ -233,6 +242,7 @@ class HybridStereoDepthExtractor:
             # the normalisation only needs a context's min/max scratch, not a matcher-sized workspace
             if getattr(self, "_aux_ctx", None) is None:
                 self._aux_ctx = _native.Context(72, 8, _native.SgbmParams(), max_batch=1, device=self.gpu_index)
+                self._aux_ctx.set_depth_scale(self.depth_scale == "fixed", 0.0, float(self.num_disparities))
             ctx = self._aux_ctx
         t = torch.from_numpy(np.ascontiguousarray(depth_map, dtype=np.float32)).to(ctx.device)[None]
         u16 = ctx.normalize_u16(t)[0].cpu().numpy().view(np.uint16)
