@@ -165,6 +165,16 @@ int v3d_depth_frames_host(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, 
 int v3d_fused_sweep_clusters(const v3d_ctx* ctx);
 /* Number of kernel launches issued through this context so far. */
 unsigned long long v3d_launch_count(const v3d_ctx* ctx);
+/* GPU-side 16-bit PNG writer (cv2.imwrite of depth.py:406 costs ~50 ms per frame and core).
+ * Packs uint16 gray images into complete IDAT payloads: a zlib stream of STORED deflate blocks (no
+ * compression) holding the filter-0 scanlines with big-endian samples, Adler-32 included.  The host only
+ * adds the fixed chunks and the IDAT CRC (video_3d_pipeline._native.png16_file_chunks) -- the decoded
+ * pixels are identical to what cv2.imwrite stores.
+ * payload: [batch][payload_stride] bytes, payload_stride >= v3d_png16_payload_bytes(w, h). */
+size_t v3d_png16_payload_bytes(int w, int h);
+int v3d_png16_pack(v3d_ctx* ctx, const uint16_t* img_u16, int w, int h, int batch, uint8_t* payload,
+                   size_t payload_stride, void* stream);
+
 /* OPT-IN behaviour change (the default reproduces the reference).
  * save_depth_map (depth.py:400-401) stretches every frame to its own min/max, so
  * the 16-bit depth scale flickers from frame to frame.  With fixed = 1 the uint16

@@ -222,3 +222,15 @@ def test_alignment_offset_semantics(tmp_path):
     f.write_text(json.dumps({"video1_path": "sbs.mkv", "video2_path": "uhd.mkv", "time_offset_seconds": -2.0}))
     assert apply_alignment_offset(str(f), "uhd.mkv", 0.5) == 0.0
     assert guide_start_frame(str(f), "uhd.mkv", 24.0) == 0
+
+
+def test_png16_container_writer_without_gpu(tmp_path):
+    """_native.png16_file_chunks / write_png16 (the host half of the GPU PNG writer) on a CPU-made payload."""
+    import zlib
+    import cv2
+    from video_3d_pipeline import _native as nv
+    img = np.random.default_rng(3).integers(0, 65536, (37, 91), dtype=np.uint16)
+    raw = b"".join(b"\x00" + img[y].astype(">u2").tobytes() for y in range(37))
+    nv.write_png16(tmp_path / "a.png", zlib.compress(raw, 0), 91, 37)
+    dec = cv2.imread(str(tmp_path / "a.png"), cv2.IMREAD_UNCHANGED)
+    assert dec.dtype == np.uint16 and np.array_equal(dec, img)

@@ -77,6 +77,14 @@ def test_process_video_sbs_and_upscale(tmp_path):
         assert np.array_equal(got, ref)
     # second call hits the cache (depth.py:435-437)
     assert ex.process_video_sbs(str(clip), start_frame=1, max_frames=3) == out_dir
+    # GPU-side PNG writer (png_compression=0): different bytes on disk, identical pixels
+    ex0 = IGEVStereoDepthExtractor(work_dir=str(tmp_path / "w0"), cache_dir=str(tmp_path / "w0"), unsqueeze_sbs=True,
+                                   batch_size=2, png_compression=0)
+    out0 = ex0.process_video_sbs(str(clip), start_frame=1, max_frames=3)
+    for i in range(3):
+        a = cv2.imread(str(out_dir / f"depth_{i:06d}.png"), cv2.IMREAD_UNCHANGED)
+        b = cv2.imread(str(out0 / f"depth_{i:06d}.png"), cv2.IMREAD_UNCHANGED)
+        assert b.dtype == np.uint16 and np.array_equal(a, b)
 
     guide_frames = [synthetic.guide_frame(22, t, 4 * W, 2 * H)[..., ::-1].copy() for t in range(3)]
     gclip = tmp_path / "g4k.avi"

@@ -81,7 +81,7 @@ void v3d_default_params(v3d_sgbm_params* p)
 static void free_all(v3d_ctx* c)
 {
     void* ptrs[] = { c->grayL, c->grayR, c->rexp, c->lexp, c->C, c->S, c->rec, c->raw, c->med, c->disp, c->labels,
-                     c->sizes, c->minmax, c->f32_tmp, c->u16_tmp, c->ab, c->in_dev, c->guide_dev, c->out_dev };
+                     c->sizes, c->minmax, c->png_sums, c->f32_tmp, c->u16_tmp, c->ab, c->in_dev, c->guide_dev, c->out_dev };
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -147,7 +147,7 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
         { (void**)&c->rec, B * (size_t)eye_h * c->W1 * sizeof(uint2) },
         { (void**)&c->raw, B * npx * 2 }, { (void**)&c->med, B * npx * 2 }, { (void**)&c->disp, B * npx * 2 },
         { (void**)&c->labels, B * npx * 4 }, { (void**)&c->sizes, B * npx * 4 },
-        { (void**)&c->minmax, B * 2 * sizeof(int) },
+        { (void**)&c->minmax, B * 2 * sizeof(int) }, { (void**)&c->png_sums, B * 2 * sizeof(unsigned long long) },
         { (void**)&c->f32_tmp, B * npx * 4 }, { (void**)&c->u16_tmp, B * npx * 2 },
     };
     for (auto& a : allocs) {
@@ -186,6 +186,24 @@ int v3d_set_debug_taps(v3d_ctx* ctx, int enabled)
     if (!ctx) return v3d_fail(V3D_EINVAL, "null context");
     ctx->debug_taps = enabled != 0;
     return V3D_OK;
+}
+
+size_t v3d_png16_payload_bytes(int w, int h)
+{
+    if (w <= 0 || h <= 0) return 0;
+    const size_t n = v3d_png16_raw_bytes(w, h);
+    return 2 + 5 * ((n + 65534) / 65535) + n + 4;       // zlib header, stored-block headers, scanlines, Adler-32
+}
+
+int v3d_png16_pack(v3d_ctx* ctx, const uint16_t* img_u16, int w, int h, int batch, uint8_t* payload,
+                   size_t payload_stride, void* stream)
+{
+    if (!ctx || !img_u16 || !payload) return v3d_fail(V3D_EINVAL, "null argument");
+    if (w <= 0 || h <= 0 || batch <= 0 || batch > ctx->max_batch) return v3d_fail(V3D_EINVAL, "bad size / batch");
+    if (v3d_png16_raw_bytes(w, h) >= (1ull << 32)) return v3d_fail(V3D_EINVAL, "image too large for one IDAT chunk");
+    if (payload_stride < v3d_png16_payload_bytes(w, h)) return v3d_fail(V3D_EINVAL, "payload_stride too small");
+    V3D_CUDA(cudaSetDevice(ctx->device));
+    return v3d_launch_png16_pack(ctx, img_u16, w, h, batch, payload, payload_stride, (cudaStream_t)stream);
 }
 
 int v3d_set_depth_scale(v3d_ctx* ctx, int fixed, float lo, float hi)

@@ -32,6 +32,7 @@ struct v3d_ctx {
     int16_t *raw, *med, *disp;   // [B][H][W]
     int *labels, *sizes;         // [B][H*W]
     int* minmax;                 // [B][2]
+    unsigned long long* png_sums; // [B][2] Adler-32 partial sums of v3d_png16_pack
     float* f32_tmp;              // [B][H][W]
     uint16_t* u16_tmp;           // [B][H][W]
     // lazily sized buffers
@@ -91,6 +92,11 @@ int v3d_launch_speckle(v3d_ctx* ctx, int batch, int16_t* disp, size_t dpitch, si
 int v3d_launch_post(v3d_ctx* ctx, const int16_t* disp, size_t dpitch, size_t dstride, int batch,
                     float* f32, uint16_t* u16, cudaStream_t st);
 int v3d_launch_normalize_f32(v3d_ctx* ctx, const float* in, size_t n, int batch, uint16_t* out, cudaStream_t st);
+// k_png.cu
+int v3d_launch_png16_pack(v3d_ctx* ctx, const uint16_t* img, int w, int h, int batch, uint8_t* payload,
+                           size_t payload_stride, cudaStream_t st);
+size_t v3d_png16_raw_bytes(int w, int h);
+
 // k_guided.cu
 int v3d_launch_guided(v3d_ctx* ctx, const uint16_t* depth, int w, int h, const uint8_t* guide, int gw, int gh,
                       int batch, int r, float eps, uint16_t* out, float* q, cudaStream_t st);

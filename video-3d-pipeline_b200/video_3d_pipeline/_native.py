@@ -69,13 +69,16 @@ def lib():
     L.v3d_launch_count.argtypes = [vp]
     L.v3d_launch_count.restype = C.c_ulonglong
     L.v3d_set_depth_scale.argtypes = [vp, i32, C.c_float, C.c_float]
+    L.v3d_png16_payload_bytes.argtypes = [i32, i32]
+    L.v3d_png16_payload_bytes.restype = sz
+    L.v3d_png16_pack.argtypes = [vp, vp, i32, i32, i32, vp, sz, vp]
     L.v3d_set_timing.argtypes = [vp, i32]
     L.v3d_reset_timing.argtypes = [vp]
     L.v3d_stage_ms.argtypes = [vp, i32, C.POINTER(C.c_char_p)]
     L.v3d_stage_ms.restype = C.c_double
     for name in ("v3d_create", "v3d_destroy", "v3d_split_gray", "v3d_bgr_to_gray", "v3d_unsqueeze_bgr",
                  "v3d_sgbm_compute", "v3d_set_debug_taps", "v3d_debug_tap", "v3d_debug_tap_copy", "v3d_postprocess", "v3d_normalize_u16",
-                 "v3d_guided_upscale", "v3d_depth_frames", "v3d_depth_frames_host", "v3d_set_depth_scale", "v3d_set_timing",
+                 "v3d_guided_upscale", "v3d_depth_frames", "v3d_depth_frames_host", "v3d_set_depth_scale", "v3d_png16_pack", "v3d_set_timing",
                  "v3d_reset_timing"):
         getattr(L, name).restype = i32
     _lib = L
@@ -95,6 +98,30 @@ def _raise(rc, what):
 def _check(rc, what):
     if rc != 0:
         _raise(rc, what)
+
+
+_PNG_SIG = b"\x89PNG\r\n\x1a\n"
+
+
+def _png_chunk(tag: bytes, body) -> list:
+    import struct
+    import zlib
+    crc = zlib.crc32(body, zlib.crc32(tag)) & 0xFFFFFFFF
+    return [struct.pack(">I", len(body)), tag, body, struct.pack(">I", crc)]
+
+
+def png16_file_chunks(payload, w: int, h: int) -> list:
+    """The byte strings of a complete 16-bit grayscale PNG whose IDAT content is `payload` (a zlib stream of
+    the filter-0 scanlines, e.g. one row of Context.png16_pack brought to the host).  The only per-pixel work
+    left on the CPU is the CRC-32 of the IDAT chunk (zlib.crc32 releases the GIL)."""
+    import struct
+    ihdr = struct.pack(">IIBBBBB", int(w), int(h), 16, 0, 0, 0, 0)      # 16 bit, gray, deflate, adaptive, no interlace
+    return [_PNG_SIG] + _png_chunk(b"IHDR", ihdr) + _png_chunk(b"IDAT", payload) + _png_chunk(b"IEND", b"")
+
+
+def write_png16(path, payload, w: int, h: int):
+    with open(path, "wb") as f:
+        f.writelines(png16_file_chunks(payload, w, h))
 
 
 def require_cuda():
@@ -167,6 +194,19 @@ class Context:
     @property
     def fused_sweep_clusters(self):
         return int(lib().v3d_fused_sweep_clusters(self._h))
+
+    def png16_pack(self, img_u16, out=None):
+        """uint16 [B,h,w] CUDA tensor -> uint8 [B,P] IDAT payloads (stored-deflate zlib streams, Adler-32
+        included); png16_file_chunks() turns one payload into a .png file."""
+        if not (img_u16.is_cuda and img_u16.is_contiguous() and img_u16.dtype == torch.uint16 and img_u16.dim() == 3):
+            raise ValueError("img_u16 must be a contiguous uint16 CUDA tensor [B, h, w]")
+        B, h, w = img_u16.shape
+        P = int(lib().v3d_png16_payload_bytes(w, h))
+        if out is None:
+            out = torch.empty((B, P), dtype=torch.uint8, device=img_u16.device)
+        _check(lib().v3d_png16_pack(self._h, img_u16.data_ptr(), w, h, B, out.data_ptr(), out.stride(0),
+                                    _stream(img_u16.device)), "v3d_png16_pack")
+        return out
 
     def set_depth_scale(self, fixed, lo=0.0, hi=1.0):
         """Opt-in clip-level uint16 scale: u16 = trunc(clip((d - lo) / (hi - lo), 0, 1) * 65535).

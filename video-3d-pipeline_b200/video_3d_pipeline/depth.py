@@ -65,7 +65,9 @@ class HybridStereoDepthExtractor:
         self.gpu_index = int(gpu_index)
         self.decode_threads = int(decode_threads)      # host pipeline knobs
         self.png_threads = int(png_threads)
-        self.png_compression = int(png_compression)    # zlib level of the 16-bit PNGs; pixels are identical
+        # zlib level of the 16-bit PNGs (pixels are identical at every level).  0 = stored blocks, produced by
+        # the GPU-side writer (v3d_png16_pack): ~4 MB files at 1080p, but no libpng / deflate work on the host
+        self.png_compression = int(png_compression)
         # "frame": per-frame min-max like the reference (depth.py:400-401).  "fixed": opt-in clip-level scale
         # 0..numDisparities px -> 0..65535, so the depth scale does not flicker between frames.
         if depth_scale not in ("frame", "fixed"):
@@ -323,6 +325,7 @@ class HybridStereoDepthExtractor:
         pinned = {}
         done = 0
         png_args = [cv2.IMWRITE_PNG_COMPRESSION, int(self.png_compression)]
+        gpu_png = int(self.png_compression) == 0        # level 0 = stored: packed on the GPU, no libpng on the host
         try:
             for t in threads:
                 t.start()
@@ -350,11 +353,28 @@ class HybridStereoDepthExtractor:
                 host_np = host.numpy()
                 for i, f in enumerate(batch):
                     np.copyto(host_np[i], f)
-                ctx.depth_frames_host(host, self.unsqueeze_sbs, out={"u16": u16})
-                maps = u16.numpy().view(np.uint16)
-                for i in range(n):
-                    path = cache_path / f"depth_{out_index + i:06d}.png"
-                    pending.append(pool.submit(cv2.imwrite, str(path), maps[i].copy(), png_args))
+                if gpu_png:
+                    # GPU-side writer: the kernels leave complete IDAT payloads (stored deflate + Adler-32);
+                    # the pool threads add the fixed chunks and one CRC-32 and write the file
+                    if pinned.get("png_key") != key:
+                        pinned["png_key"] = key
+                        P = int(_native.lib().v3d_png16_payload_bytes(eye_w, h))
+                        pinned["png"] = torch.empty((ctx.max_batch, P), dtype=torch.uint8).pin_memory()
+                    dev = torch.device("cuda", self.gpu_index)
+                    res = ctx.depth_frames(host.to(dev, non_blocking=True), self.unsqueeze_sbs, want=("u16",))
+                    pay = pinned["png"][:n]
+                    pay.copy_(ctx.png16_pack(res["u16"]), non_blocking=True)
+                    torch.cuda.current_stream(dev).synchronize()
+                    pay_np = pay.numpy()
+                    for i in range(n):
+                        path = cache_path / f"depth_{out_index + i:06d}.png"
+                        pending.append(pool.submit(_native.write_png16, str(path), pay_np[i].tobytes(), eye_w, h))
+                else:
+                    ctx.depth_frames_host(host, self.unsqueeze_sbs, out={"u16": u16})
+                    maps = u16.numpy().view(np.uint16)
+                    for i in range(n):
+                        path = cache_path / f"depth_{out_index + i:06d}.png"
+                        pending.append(pool.submit(cv2.imwrite, str(path), maps[i].copy(), png_args))
                 done += n
                 print(f"✓ Saved batch depth maps ({done}/{count} total)")
             for f in pending:
