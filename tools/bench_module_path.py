@@ -1,6 +1,6 @@
 """Wall-clock of the reference-facing module path (decode -> GPU -> PNG16), SURVEY 8(f) item 1.
 
-    python tools/bench_module_path.py [frames]
+    python tools/bench_module_path.py [frames] [decode threads] [png compression; 0 = GPU-side stored PNG] [gpu lanes]
 
 Writes a synthetic full-SBS 3840x1080 MJPG clip, runs IGEVStereoDepthExtractor.process_video_sbs on it
 (unsqueeze off, D=128) and reports frames/s with the time split into decode, GPU call and PNG encode.
@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "video-3d-pipeline_b200"))
 import cv2, numpy as np
 
-def main(n=64, decode_threads=4):
+def main(n=64, decode_threads=4, png_compression=1, gpu_lanes=2):
     from video_3d_pipeline import synthetic
     from video_3d_pipeline.depth import IGEVStereoDepthExtractor
     tmp = Path(tempfile.mkdtemp(prefix="v3d_mod_"))
@@ -36,13 +36,14 @@ def main(n=64, decode_threads=4):
     t_png = (time.perf_counter() - t0) / 8
     ex = IGEVStereoDepthExtractor(work_dir=str(tmp / "w"), cache_dir=str(tmp / "w"), unsqueeze_sbs=False,
                                   batch_size=16, stereo_only=True, num_disparities=128,
-                                  decode_threads=decode_threads)
-    ex.process_video_sbs(str(clip), max_frames=16, force_reprocess=True)        # warm-up (context, kernels)
+                                  decode_threads=decode_threads, png_compression=png_compression, gpu_lanes=gpu_lanes)
+    ex.process_video_sbs(str(clip), max_frames=min(n, 32 * gpu_lanes), force_reprocess=True)   # warm-up: every lane's context
     t0 = time.perf_counter()
     out = ex.process_video_sbs(str(clip), force_reprocess=True)
     wall = time.perf_counter() - t0
-    print(json.dumps({"decode_threads": decode_threads, "frames": k, "module_path_fps": round(k / wall, 1), "decode_only_fps": round(k / t_dec, 1),
+    print(json.dumps({"decode_threads": decode_threads, "png_compression": png_compression, "gpu_lanes": gpu_lanes, "frames": k, "module_path_fps": round(k / wall, 1), "decode_only_fps": round(k / t_dec, 1),
                       "png16_encode_ms_per_frame_one_core": round(t_png * 1000, 1), "out_dir_files": len(list(out.glob('*.png')))}))
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 64, int(sys.argv[2]) if len(sys.argv) > 2 else 4)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 64, int(sys.argv[2]) if len(sys.argv) > 2 else 4,
+         int(sys.argv[3]) if len(sys.argv) > 3 else 1, int(sys.argv[4]) if len(sys.argv) > 4 else 2)

@@ -49,7 +49,8 @@ class HybridStereoDepthExtractor:
                  decode_threads: int = 4,
                  png_threads: int = 8,
                  png_compression: int = 1,
-                 depth_scale: str = "frame"):
+                 depth_scale: str = "frame",
+                 gpu_lanes: int = 2):
         # depth.py:33-40
         self.device = device
         self.work_dir = create_work_directory(work_dir)
@@ -73,6 +74,7 @@ class HybridStereoDepthExtractor:
         if depth_scale not in ("frame", "fixed"):
             raise ValueError(f"depth_scale must be 'frame' or 'fixed', not {depth_scale!r}")
         self.depth_scale = depth_scale
+        self.gpu_lanes = max(1, int(gpu_lanes))        # consumer threads (own context + stream) of process_video_sbs
 
         if not str(device).startswith("cuda"):
             raise RuntimeError(f"device {device!r}: this build has no CPU path, use device='cuda'")
@@ -91,6 +93,7 @@ class HybridStereoDepthExtractor:
         self.max_vram_usage = 0.9
         self.memory_stats = defaultdict(float)
         self._ctx = None
+        self._lane_ctx = {}
 
     # ------------------------------------------------------------------ model / context
     def load_model(self):
@@ -107,14 +110,17 @@ class HybridStereoDepthExtractor:
         """The literals of depth.py:315-325 with D / mode from the constructor."""
         return _native.SgbmParams(numDisparities=self.num_disparities, mode=self.sgbm_mode)
 
-    def _context(self, eye_w: int, eye_h: int, batch: int) -> _native.Context:
-        c = self._ctx
+    def _context(self, eye_w: int, eye_h: int, batch: int, lane: int = 0) -> _native.Context:
+        c = self._lane_ctx.get(lane)
         if c is None or (c.W, c.H) != (eye_w, eye_h) or c.max_batch < batch:
             if c is not None:
                 c.close()
-            self._ctx = c = _native.Context(eye_w, eye_h, self.sgbm_params(),
-                                            max_batch=max(batch, self.batch_size), device=self.gpu_index)
+            c = _native.Context(eye_w, eye_h, self.sgbm_params(),
+                                max_batch=max(batch, self.batch_size), device=self.gpu_index)
             c.set_depth_scale(self.depth_scale == "fixed", 0.0, float(self.num_disparities))
+            self._lane_ctx[lane] = c
+            if lane == 0:
+                self._ctx = c
         return c
 
     # ------------------------------------------------------------------ cache (depth.py:116-140)
@@ -322,65 +328,93 @@ class HybridStereoDepthExtractor:
         threads = [threading.Thread(target=reader, args=sl, daemon=True) for sl in slices]
         pool = ThreadPoolExecutor(max_workers=max(2, int(self.png_threads)))    # PNG encoding releases the GIL
         pending = []
-        pinned = {}
-        done = 0
+        plock = threading.Lock()
+        progress = {"done": 0}
         png_args = [cv2.IMWRITE_PNG_COMPRESSION, int(self.png_compression)]
         gpu_png = int(self.png_compression) == 0        # level 0 = stored: packed on the GPU, no libpng on the host
+        dev = torch.device("cuda", self.gpu_index)
+        n_lanes = max(1, min(self.gpu_lanes, (count + bs - 1) // bs))
+        work: "queue.Queue" = queue.Queue(maxsize=n_lanes)
+        errors = []
+
+        def run_batch(lane: int, pinned: dict, out_index: int, batch):
+            n = len(batch)
+            h, w = batch[0].shape[:2]
+            if w % 2:
+                raise ValueError("SBS frame width must be even")           # depth.py:254-255
+            eye_w = w if self.unsqueeze_sbs else w // 2
+            ctx = self._context(eye_w, h, n, lane)
+            key = (ctx.max_batch, h, w, eye_w)
+            if pinned.get("key") != key:           # pinned staging buffers are allocated once, not per batch
+                pinned["key"] = key
+                pinned["in"] = torch.empty((ctx.max_batch, h, w, 3), dtype=torch.uint8).pin_memory()
+                pinned["out"] = torch.empty((ctx.max_batch, h, eye_w), dtype=torch.uint16).pin_memory()
+                if gpu_png:
+                    P = int(_native.lib().v3d_png16_payload_bytes(eye_w, h))
+                    pinned["png"] = torch.empty((ctx.max_batch, P), dtype=torch.uint8).pin_memory()
+            host, u16 = pinned["in"][:n], pinned["out"][:n]
+            host_np = host.numpy()
+            for i, f in enumerate(batch):
+                np.copyto(host_np[i], f)
+            futures = []
+            if gpu_png:
+                # GPU-side writer: the kernels leave complete IDAT payloads (stored deflate + Adler-32);
+                # the pool threads add the fixed chunks and one CRC-32 and write the file
+                res = ctx.depth_frames(host.to(dev, non_blocking=True), self.unsqueeze_sbs, want=("u16",))
+                pay = pinned["png"][:n]
+                pay.copy_(ctx.png16_pack(res["u16"]), non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                pay_np = pay.numpy()
+                for i in range(n):
+                    path = cache_path / f"depth_{out_index + i:06d}.png"
+                    futures.append(pool.submit(_native.write_png16, str(path), pay_np[i].tobytes(), eye_w, h))
+            else:
+                ctx.depth_frames_host(host, self.unsqueeze_sbs, out={"u16": u16})
+                maps = u16.numpy().view(np.uint16)
+                for i in range(n):
+                    path = cache_path / f"depth_{out_index + i:06d}.png"
+                    futures.append(pool.submit(cv2.imwrite, str(path), maps[i].copy(), png_args))
+            with plock:
+                pending.extend(futures)
+                progress["done"] += n
+                print(f"✓ Saved batch depth maps ({progress['done']}/{count} total)")
+
+        def consumer(lane: int):
+            # one lane = one context + one stream + its own pinned staging: the host copies of one lane overlap
+            # the kernels of the other
+            pinned = {}
+            try:
+                with torch.cuda.device(dev), torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                    while True:
+                        item = work.get()
+                        if item is None:
+                            return
+                        if not errors:
+                            run_batch(lane, pinned, *item)
+            except BaseException as e:
+                errors.append(e)
+                while work.get() is not None:          # keep draining so the dispatcher never blocks
+                    pass
+
+        lanes = [threading.Thread(target=consumer, args=(k,), daemon=True) for k in range(n_lanes)]
         try:
-            for t in threads:
+            for t in threads + lanes:
                 t.start()
             live = len(threads)
-            while live:
+            while live and not errors:
                 item = q.get()
                 if item is None:
                     live -= 1
                     continue
                 if isinstance(item, BaseException):
                     raise item
-                out_index, batch = item
-                n = len(batch)
-                h, w = batch[0].shape[:2]
-                if w % 2:
-                    raise ValueError("SBS frame width must be even")           # depth.py:254-255
-                eye_w = w if self.unsqueeze_sbs else w // 2
-                ctx = self._context(eye_w, h, n)
-                key = (ctx.max_batch, h, w, eye_w)
-                if pinned.get("key") != key:           # pinned staging buffers are allocated once, not per batch
-                    pinned["key"] = key
-                    pinned["in"] = torch.empty((ctx.max_batch, h, w, 3), dtype=torch.uint8).pin_memory()
-                    pinned["out"] = torch.empty((ctx.max_batch, h, eye_w), dtype=torch.uint16).pin_memory()
-                host, u16 = pinned["in"][:n], pinned["out"][:n]
-                host_np = host.numpy()
-                for i, f in enumerate(batch):
-                    np.copyto(host_np[i], f)
-                if gpu_png:
-                    # GPU-side writer: the kernels leave complete IDAT payloads (stored deflate + Adler-32);
-                    # the pool threads add the fixed chunks and one CRC-32 and write the file
-                    if pinned.get("png_key") != key:
-                        pinned["png_key"] = key
-                        P = int(_native.lib().v3d_png16_payload_bytes(eye_w, h))
-                        pinned["png"] = torch.empty((ctx.max_batch, P), dtype=torch.uint8).pin_memory()
-                    dev = torch.device("cuda", self.gpu_index)
-                    res = ctx.depth_frames(host.to(dev, non_blocking=True), self.unsqueeze_sbs, want=("u16",))
-                    pay = pinned["png"][:n]
-                    pay.copy_(ctx.png16_pack(res["u16"]), non_blocking=True)
-                    torch.cuda.current_stream(dev).synchronize()
-                    pay_np = pay.numpy()
-                    for i in range(n):
-                        path = cache_path / f"depth_{out_index + i:06d}.png"
-                        pending.append(pool.submit(_native.write_png16, str(path), pay_np[i].tobytes(), eye_w, h))
-                else:
-                    ctx.depth_frames_host(host, self.unsqueeze_sbs, out={"u16": u16})
-                    maps = u16.numpy().view(np.uint16)
-                    for i in range(n):
-                        path = cache_path / f"depth_{out_index + i:06d}.png"
-                        pending.append(pool.submit(cv2.imwrite, str(path), maps[i].copy(), png_args))
-                done += n
-                print(f"✓ Saved batch depth maps ({done}/{count} total)")
-            for f in pending:
-                f.result()
+                work.put(item)
         finally:
             stop.set()
+            for _ in lanes:
+                work.put(None)
+            for t in lanes:
+                t.join()
             while any(t.is_alive() for t in threads):          # unblock readers stuck on a full queue
                 try:
                     q.get_nowait()
@@ -388,8 +422,15 @@ class HybridStereoDepthExtractor:
                     pass
                 for t in threads:
                     t.join(timeout=0.01)
-            pool.shutdown(wait=True)
-        return done
+            try:
+                if not errors:
+                    for f in pending:
+                        f.result()
+            finally:
+                pool.shutdown(wait=True)
+        if errors:
+            raise errors[0]
+        return progress["done"]
 
 
 # run_pipeline.py:12 and the reference's __init__.py:6 import this name, which the reference's

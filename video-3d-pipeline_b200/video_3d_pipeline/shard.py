@@ -36,7 +36,7 @@ def _worker(rank: int, cfg: dict, ret):
         device="cuda", batch_size=cfg["batch_size"], use_neural_guidance=False, stereo_only=True,
         unsqueeze_sbs=cfg["unsqueeze_sbs"], num_disparities=cfg["num_disparities"], sgbm_mode=cfg["sgbm_mode"],
         num_gpus=1, gpu_index=rank, decode_threads=cfg["decode_threads"], png_threads=cfg["png_threads"],
-        png_compression=cfg["png_compression"], depth_scale=cfg["depth_scale"])
+        png_compression=cfg["png_compression"], depth_scale=cfg["depth_scale"], gpu_lanes=cfg["gpu_lanes"])
     ex.load_model()
     start, n = cfg["ranges"][rank]
     done = 0
@@ -57,7 +57,7 @@ def run_sharded(extractor, video_path: str, first: int, count: int, cache_path: 
                unsqueeze_sbs=extractor.unsqueeze_sbs, num_disparities=extractor.num_disparities,
                sgbm_mode=extractor.sgbm_mode, decode_threads=extractor.decode_threads,
                png_threads=extractor.png_threads, png_compression=extractor.png_compression,
-               depth_scale=extractor.depth_scale, ranges=ranges, first=first, video_path=video_path,
+               depth_scale=extractor.depth_scale, gpu_lanes=extractor.gpu_lanes, ranges=ranges, first=first, video_path=video_path,
                cache_path=str(cache_path))
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
