@@ -50,12 +50,12 @@ CELLS = W1 * EYE_H * D
 ALG_IOPS = (31 + 9 * 5) * CELLS                          # 18.8 Gop
 # DRAM bytes per frame measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 15-frame launch / 15), see profiles/README.md; keyed by bench stage.
-NCU_DRAM_BYTES_PER_FRAME = {      # profiles/r01_final_ncu_full_top6.csv
-    "cost": (1.981910e9 + 7.375967e9) / 15,
-    "vertical": (7.433441e9 + 7.386856e9) / 15,
-    "lr": (14.864263e9 + 7.392594e9) / 15,
-    "wta": (14.863643e9 + 0.237814e9) / 15,
-    "guided": (0.452210e9 + 1.938373e9 + 2.407520e9 + 0.244936e9) / 2 / 15,
+NCU_DRAM_BYTES_PER_FRAME = {      # profiles/r01b_ncu_full_top6.csv
+    "cost": (1.981027e9 + 7.375259e9) / 15,
+    "vertical": (7.431941e9 + 7.386773e9) / 15,
+    "lr": (14.863835e9 + 7.394008e9) / 15,
+    "wta": (14.863620e9 + 0.237158e9) / 15,
+    "guided": (0.451309e9 + 1.939497e9 + 2.407548e9 + 0.245043e9) / 2 / 15,
 }
 
 
@@ -419,7 +419,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0,
-                    help="frames per step per GPU (default: lanes x the co-resident clusters of the fused sweep, 45 on most B200s)")
+                    help="frames per step per GPU (default: lanes x the co-resident clusters of the fused sweep, 75 on most B200s)")
     ap.add_argument("--lanes", type=int, default=5, help="streams/contexts the batch is split over")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
