@@ -36,24 +36,32 @@ __device__ __forceinline__ void prefilter_px(const uint8_t* img, size_t pitch, i
     inten = gray_at(img, pitch, H, x, y);
 }
 
-__device__ __forceinline__ uint2 prefilter_rec(const uint8_t* img, size_t pitch, int W, int H, int x, int y, int ftzero)
+// BT half-pixel interval record {v | lo << 8 | hi << 16} of one channel from the pixel and its two neighbours
+// (-1 = neighbour outside the image)
+__device__ __forceinline__ uint32_t bt_interval(int pm, int v, int pp)
 {
-    if (x < 0 || x >= W) return make_uint2(0, 0);
-    int s[3], t[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const int xx = x - 1 + i;
-        if (xx < 0 || xx >= W) { s[i] = -1; t[i] = -1; }     // missing neighbour
-        else prefilter_px(img, pitch, W, H, xx, y, ftzero, s[i], t[i]);
-    }
-    auto interval = [](const int (&p)[3]) -> uint32_t {
-        const int v = p[1];
-        const int l = p[0] >= 0 ? (v + p[0]) >> 1 : v;
-        const int r = p[2] >= 0 ? (v + p[2]) >> 1 : v;
-        const int lo = min(v, min(l, r)), hi = max(v, max(l, r));
-        return (uint32_t)v | ((uint32_t)lo << 8) | ((uint32_t)hi << 16);
-    };
-    return make_uint2(interval(s), interval(t));
+    const int l = pm >= 0 ? (v + pm) >> 1 : v;
+    const int r = pp >= 0 ? (v + pp) >> 1 : v;
+    const int lo = min(v, min(l, r)), hi = max(v, max(l, r));
+    return (uint32_t)v | ((uint32_t)lo << 8) | ((uint32_t)hi << 16);
+}
+
+// prefiltered pixel as sobel | intensity << 8, or 0xffff outside the image
+__device__ __forceinline__ uint32_t prefilter_packed(const uint8_t* img, size_t pitch, int W, int H, int x, int y, int ftzero)
+{
+    if (x < 0 || x >= W) return 0xffffu;
+    int sob, inten;
+    prefilter_px(img, pitch, W, H, x, y, ftzero, sob, inten);
+    return (uint32_t)sob | ((uint32_t)inten << 8);
+}
+
+// record of the pixel whose packed value is `c`, with packed neighbours `m` (x-1) and `p` (x+1); zero outside
+__device__ __forceinline__ uint2 rec_from_packed(uint32_t m, uint32_t c, uint32_t p)
+{
+    if (c == 0xffffu) return make_uint2(0, 0);
+    const int sm = m == 0xffffu ? -1 : (int)(m & 0xff), im = m == 0xffffu ? -1 : (int)(m >> 8);
+    const int sp = p == 0xffffu ? -1 : (int)(p & 0xff), ip = p == 0xffffu ? -1 : (int)(p >> 8);
+    return make_uint2(bt_interval(sm, (int)(c & 0xff), sp), bt_interval(im, (int)(c >> 8), ip));
 }
 
 __device__ __forceinline__ uint32_t neg16(uint32_t v) { return (0x10000u - v) & 0xffffu; }
@@ -73,14 +81,28 @@ __global__ void __launch_bounds__(256)
 k_prefilter_expand(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, size_t gpitch, size_t gstride,
                    int W, int H, int ftzero, uint4* __restrict__ rexp, int wpw, uint4* __restrict__ lexp)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // Every pixel is prefiltered once per block into shared memory (the 3-pixel intervals of neighbouring
+    // outputs overlap: per-thread evaluation costs 4x the loads and Sobel arithmetic).
+    constexpr int NRC = 2 * 256 + 4;               // right-image columns a block touches: xmax+1 down to xmax-514
+    constexpr int NLC = 256 + 2;                   // left-image columns: lb .. lb+257, lb = min(t0-1, W-2)
+    __shared__ uint16_t pr[NRC], pl[NLC];
+    const int t0 = blockIdx.x * 256, t = t0 + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z;
+    const uint8_t* imgR = right + (size_t)b * gstride;
+    const uint8_t* imgL = left + (size_t)b * gstride;
+    const int xmax = W - 1 - (2 * t0 - PADL);      // column of element 2*t0 (the block's right-most one)
+    const int lb = min(t0 - 1, W - 2);             // blocks past the image only repeat its last column
+    if (t0 < wpw)
+        for (int i = threadIdx.x; i < NRC; i += 256) pr[i] = (uint16_t)prefilter_packed(imgR, gpitch, W, H, xmax + 1 - i, y, ftzero);
+    if (t0 < W + TXW)
+        for (int i = threadIdx.x; i < NLC; i += 256) pl[i] = (uint16_t)prefilter_packed(imgL, gpitch, W, H, lb + i, y, ftzero);
+    __syncthreads();
     if (t < wpw) {
-        const uint8_t* img = right + (size_t)b * gstride;
-        const int xr0 = W - 1 - (2 * t - PADL);                    // column of element 2t
+        // elements 2t, 2t+1, 2t+2 = columns xr0, xr0-1, xr0-2 with xr0 = xmax - 2*threadIdx.x; column x sits at pr[xmax+1-x]
+        const int i0 = 1 + 2 * threadIdx.x;
         uint2 rec[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) rec[i] = prefilter_rec(img, gpitch, W, H, xr0 - i, y, ftzero);
+        for (int i = 0; i < 3; i++) rec[i] = rec_from_packed(pr[i0 + i + 1], pr[i0 + i], pr[i0 + i - 1]);
         uint4* base = rexp + ((size_t)(b * H + y) * 4) * wpw + t;
         base[0 * (size_t)wpw] = pack_quads(rec[0].x, rec[1].x);    // channel 0 (sobel), copy 0: elements 2t, 2t+1
         base[1 * (size_t)wpw] = pack_quads(rec[1].x, rec[2].x);    // channel 0, copy 1: elements 2t+1, 2t+2
@@ -88,8 +110,8 @@ k_prefilter_expand(const uint8_t* __restrict__ left, const uint8_t* __restrict__
         base[3 * (size_t)wpw] = pack_quads(rec[1].y, rec[2].y);
     }
     if (t < W + TXW) {
-        const uint8_t* img = left + (size_t)b * gstride;
-        const uint2 rec = prefilter_rec(img, gpitch, W, H, min(t, W - 1), y, ftzero);
+        const int i = min(t, W - 1) - lb;                           // columns past the image repeat the last one
+        const uint2 rec = rec_from_packed(pl[i - 1], pl[i], pl[i + 1]);
         uint4* o = lexp + ((size_t)(b * H + y) * (W + TXW) + t) * 2;
         o[0] = pack_quads(rec.x, rec.x);
         o[1] = pack_quads(rec.y, rec.y);
