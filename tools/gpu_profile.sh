@@ -1,3 +1,6 @@
+# End-of-round evidence run on a GPU box: tests, smoke, default bench, reference arm, ncu launch list of the
+# default command, ncu --set full of the six largest kernels, the other BASELINE configs.  Outputs land in
+# gpurun_out/ and are summarised into profiles/ by hand.   gpurun -- bash tools/gpu_profile.sh
 set -x
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
