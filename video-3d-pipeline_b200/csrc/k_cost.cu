@@ -12,6 +12,8 @@
 #include "v3d_internal.h"
 #include "tma.cuh"
 
+#include <type_traits>
+
 namespace {
 
 constexpr int TXW = 32;       // window columns per block (one warp each); TXW - 2R of them are output columns
@@ -138,8 +140,19 @@ struct CostSmem {
     uint4 rbuf[U][2][2][NWORDS];      // [stage][channel][copy][word] = {v, -v, lo, -hi} pairs of the right image
     uint4 lbuf[U][TXW][2];            // [stage][column][channel]     = {u, -u, lo, -hi} of the left image
     uint32_t vbuf[U][TXW][D / 2];     // [slot][column][pair]         = vertical sums
-    uint64_t bar[U];
+    uint64_t bar[U];                  // TMA completion, one per staged row
+    uint64_t gbar[U / RPB];           // "every warp has written its vertical sums of this row group" (32 arrivals)
 };
+
+// compile-time unrolled loop: f(std::integral_constant<int, I>) for I in [0, N)
+template <int N, int I = 0, class F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<N, I + 1>(f);
+    }
+}
 
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
 {
@@ -189,6 +202,8 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < U; s++) mbar_init(&sm.bar[s], 1);
+#pragma unroll
+        for (int s = 0; s < U / RPB; s++) mbar_init(&sm.gbar[s], TXW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -238,44 +253,57 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     const size_t out_row = (size_t)W1 * (D / 2);
     const bool h_real = !PAD || 2 * (lane + 32 * h_k) < Dreal;     // padded disparities get a cost no real one can reach
 
+    const uint32_t gbar0 = smem_u32(&sm.gbar[0]);
+    // Phase 1 of a row group: the pixel costs of its RPB rows, the running vertical sums, their store for the
+    // horizontal pass, and this warp's arrival on the group's barrier.  pgc is a compile-time constant.
+    auto cost_rows = [&](auto pgc, uint32_t par) {
+        constexpr int pg = decltype(pgc)::value;
+#pragma unroll
+        for (int s = 0; s < RPB; s++) {
+            constexpr int dummy = 0; (void)dummy;
+            const int ph = pg + s;
+            mbar_wait_a(bar0 + ph * 8, par);
+            const uint4 ls = l_p[ph * LSTG + 0];
+            const uint4 li = l_p[ph * LSTG + 1];
+#pragma unroll
+            for (int k = 0; k < NR; k++) {
+                const uint4 rs = rs_p[ph * RSTG + 32 * k];
+                const uint4 ri = ri_p[ph * RSTG + 32 * k];
+                // {x: v, y: -v, z: lo, w: -hi}
+                uint32_t c0 = __vimax_s16x2_relu(__vadd2(ls.x, rs.w), __vadd2(rs.z, ls.y));
+                uint32_t c1 = __vimax_s16x2_relu(__vadd2(rs.x, ls.w), __vadd2(ls.z, rs.y));
+                const uint32_t bs = __vminu2(c0, c1);
+                c0 = __vimax_s16x2_relu(__vadd2(li.x, ri.w), __vadd2(ri.z, li.y));
+                c1 = __vimax_s16x2_relu(__vadd2(ri.x, li.w), __vadd2(li.z, ri.y));
+                const uint32_t bi = __vminu2(c0, c1);
+                const uint32_t pix = bs + ((bi >> 2) & 0x3fff3fffu);
+                V[k] = V[k] + pix - ring[ph % K][k];     // halves never borrow: V includes the ring slot
+                ring[ph % K][k] = pix;
+                v_p[ph * VSTG + 32 * k] = V[k];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar0 + (pg / RPB) * 8) : "memory");
+    };
+
+    // The block barrier of a group is split: a warp arrives after its cost rows, runs the cost rows of the NEXT
+    // group, and only then waits for the others and does its share of the horizontal pass -- warps drift by up to
+    // one group instead of meeting in lock-step every RPB rows.
+    cost_rows(std::integral_constant<int, 0>{}, 0u);
     uint32_t parity = 0;
     for (int row = ystart; row < yend; row += U, parity ^= 1) {
-#pragma unroll
-        for (int pg = 0; pg < U; pg += RPB) {
-            // RPB rows between two block barriers: their cost arithmetic is independent (ILP), only the
-            // running vertical sum chains them
+        static_for<U / RPB>([&](auto pgic) {
+            constexpr int pgi = decltype(pgic)::value, pg = pgi * RPB;
+            if constexpr (pgi + 1 < U / RPB) cost_rows(std::integral_constant<int, (pgi + 1) * RPB>{}, parity);
+            else if (row + U < yend) cost_rows(std::integral_constant<int, 0>{}, parity ^ 1u);
+            mbar_wait_a(gbar0 + pgi * 8, parity);   // vbuf slots of this group complete; everyone is done with the previous group's stages
+            // Refill the stages the rows of the PREVIOUS group used (U - RPB rows ahead of this one).  Issuing a
+            // row is ~80 serial instructions of one thread: it goes to warps that own no horizontal item, one
+            // row each, so that no warp is systematically later than the others at the next group barrier.
 #pragma unroll
             for (int s = 0; s < RPB; s++) {
-                constexpr int dummy = 0; (void)dummy;
-                const int ph = pg + s;
-                mbar_wait_a(bar0 + ph * 8, parity);
-                const uint4 ls = l_p[ph * LSTG + 0];
-                const uint4 li = l_p[ph * LSTG + 1];
-#pragma unroll
-                for (int k = 0; k < NR; k++) {
-                    const uint4 rs = rs_p[ph * RSTG + 32 * k];
-                    const uint4 ri = ri_p[ph * RSTG + 32 * k];
-                    // {x: v, y: -v, z: lo, w: -hi}
-                    uint32_t c0 = __vimax_s16x2_relu(__vadd2(ls.x, rs.w), __vadd2(rs.z, ls.y));
-                    uint32_t c1 = __vimax_s16x2_relu(__vadd2(rs.x, ls.w), __vadd2(ls.z, rs.y));
-                    const uint32_t bs = __vminu2(c0, c1);
-                    c0 = __vimax_s16x2_relu(__vadd2(li.x, ri.w), __vadd2(ri.z, li.y));
-                    c1 = __vimax_s16x2_relu(__vadd2(ri.x, li.w), __vadd2(li.z, ri.y));
-                    const uint32_t bi = __vminu2(c0, c1);
-                    const uint32_t pix = bs + ((bi >> 2) & 0x3fff3fffu);
-                    V[k] = V[k] + pix - ring[ph % K][k];     // halves never borrow: V includes the ring slot
-                    ring[ph % K][k] = pix;
-                    v_p[ph * VSTG + 32 * k] = V[k];
-                }
-            }
-            __syncthreads();        // vbuf slots complete; every thread is done with the previous group's stages
-            if (tid == 0) {
-#pragma unroll
-                for (int s = 0; s < RPB; s++) {
-                    // refill the stage a row of the PREVIOUS group used (U - RPB rows ahead of this one)
-                    const int r = row + pg + s;
-                    if (r + U - RPB < yend) issue(r + U - RPB, (pg + s + U - RPB) % U);
-                }
+                const int r = row + pg + s;
+                if (c == (NITEM + s) % TXW && lane == 0 && r + U - RPB < yend) issue(r + U - RPB, (pg + s + U - RPB) % U);
             }
             if (c < NITEM && h_n > 0) {
                 const int ph = pg + h_s;                    // (h_s is warp-uniform, so is everything below)
@@ -304,7 +332,7 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
                     }
                 }
             }
-        }
+        });
         h_out += (size_t)U * out_row;
     }
 }
