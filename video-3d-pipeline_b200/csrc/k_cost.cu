@@ -207,20 +207,27 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int r, int st) {               // thread 0 only: stage image row clamp(r) into stage st
+    // one thread: stage image row clamp(r) into stage st.  The five bulk copies of a row are issued in two halves
+    // (part 0: the sobel-channel copies and the tx expectation, part 1: the intensity copies and the left row)
+    // so that two different warps can share the ~80 serial instructions; part < 0 = everything
+    auto issue = [&](int r, int st, int part) {
         const int rr = min(max(r, 0), H - 1);
         const uint4* rrow = rexp + ((size_t)(b * H + rr) * 4) * wpw;
         constexpr uint32_t RB = NWORDS * 16, LB = TXW * 2 * 16;
-        mbar_expect_tx(&sm.bar[st], 4 * RB + LB);
-        bulk_g2s(&sm.rbuf[st][0][0][0], rrow + 0 * (size_t)wpw + wlo0, RB, &sm.bar[st]);
-        bulk_g2s(&sm.rbuf[st][0][1][0], rrow + 1 * (size_t)wpw + wlo1, RB, &sm.bar[st]);
-        bulk_g2s(&sm.rbuf[st][1][0][0], rrow + 2 * (size_t)wpw + wlo0, RB, &sm.bar[st]);
-        bulk_g2s(&sm.rbuf[st][1][1][0], rrow + 3 * (size_t)wpw + wlo1, RB, &sm.bar[st]);
-        bulk_g2s(&sm.lbuf[st][0][0], lexp + ((size_t)(b * H + rr) * (W + TXW) + Xl0) * 2, LB, &sm.bar[st]);
+        if (part != 1) {
+            mbar_expect_tx(&sm.bar[st], 4 * RB + LB);
+            bulk_g2s(&sm.rbuf[st][0][0][0], rrow + 0 * (size_t)wpw + wlo0, RB, &sm.bar[st]);
+            bulk_g2s(&sm.rbuf[st][0][1][0], rrow + 1 * (size_t)wpw + wlo1, RB, &sm.bar[st]);
+        }
+        if (part != 0) {
+            bulk_g2s(&sm.rbuf[st][1][0][0], rrow + 2 * (size_t)wpw + wlo0, RB, &sm.bar[st]);
+            bulk_g2s(&sm.rbuf[st][1][1][0], rrow + 3 * (size_t)wpw + wlo1, RB, &sm.bar[st]);
+            bulk_g2s(&sm.lbuf[st][0][0], lexp + ((size_t)(b * H + rr) * (W + TXW) + Xl0) * 2, LB, &sm.bar[st]);
+        }
     };
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < U - RPB; s++) issue(ystart + s, s);   // U-RPB rows in flight
+        for (int s = 0; s < U - RPB; s++) issue(ystart + s, s, -1);   // U-RPB rows in flight
     }
 
     uint32_t ring[K][NR];
@@ -298,12 +305,15 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
             else if (row + U < yend) cost_rows(std::integral_constant<int, 0>{}, parity ^ 1u);
             mbar_wait_a(gbar0 + pgi * 8, parity);   // vbuf slots of this group complete; everyone is done with the previous group's stages
             // Refill the stages the rows of the PREVIOUS group used (U - RPB rows ahead of this one).  Issuing a
-            // row is ~80 serial instructions of one thread: it goes to warps that own no horizontal item, one
-            // row each, so that no warp is systematically later than the others at the next group barrier.
+            // row is ~80 serial instructions of one thread: it goes, in two halves, to warps that own no
+            // horizontal item, so that no warp is systematically later than the others at the next group barrier.
 #pragma unroll
             for (int s = 0; s < RPB; s++) {
                 const int r = row + pg + s;
-                if (c == (NITEM + s) % TXW && lane == 0 && r + U - RPB < yend) issue(r + U - RPB, (pg + s + U - RPB) % U);
+                if (lane == 0 && r + U - RPB < yend) {
+                    if (c == (NITEM + 2 * s) % TXW) issue(r + U - RPB, (pg + s + U - RPB) % U, 0);
+                    if (c == (NITEM + 2 * s + 1) % TXW) issue(r + U - RPB, (pg + s + U - RPB) % U, 1);
+                }
             }
             if (c < NITEM && h_n > 0) {
                 const int ph = pg + h_s;                    // (h_s is warp-uniform, so is everything below)
