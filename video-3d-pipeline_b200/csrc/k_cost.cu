@@ -16,6 +16,9 @@
 
 namespace {
 
+#ifndef V3D_COST_HN
+#define V3D_COST_HN 4
+#endif
 constexpr int TXW = 32;       // window columns per block (one warp each); TXW - 2R of them are output columns
 constexpr int PADL = 32;      // front padding (elements) of the reversed right-image rows
 
@@ -249,7 +252,7 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     constexpr int VSTG = TXW * (D / 2);
     // Horizontal sum: warp c owns one (row of the group, run of HN output columns, register k) item.  The
     // HN + 2R columns a run touches are loaded once and the window slides in registers.
-    constexpr int HN = 4, NRUN = (TX + HN - 1) / HN, NITEM = RPB * NRUN * NR;
+    constexpr int HN = V3D_COST_HN, NRUN = (TX + HN - 1) / HN, NITEM = RPB * NRUN * NR;
     static_assert(NITEM <= TXW, "one horizontal item per warp");
     const int h_s = c / (NRUN * NR), h_run = (c % (NRUN * NR)) / NR, h_k = c % NR;
     const int h_x = xs + h_run * HN;                               // first output column (window coordinates)
