@@ -137,17 +137,13 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     constexpr int PARSTRIDE = V3_NW * 2 * 32;         // inbox elements per buffer
     const int nv = min(max(W1 - gcol0, 0), CPW);      // columns of this warp inside the window
     const bool has_right = gcol0 + CPW < W1;          // a column to the right of this warp's last one exists
-    VT cq[CPW], sq[CPW];
+    VT cq[CPW];
     {
         const int y = sy > 0 ? 0 : H - 1;
         const VT* Crow = C + ((size_t)y * W1 + gcol0) * 32;
-        const VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
 #pragma unroll
         for (int j = 0; j < CPW; j++)
-            if (j < nv) {
-                cq[j] = __ldg(Crow + j * 32);
-                if (SMODE == S_ACCUM) sq[j] = Srow[j * 32];
-            }
+            if (j < nv) cq[j] = __ldg(Crow + j * 32);
     }
     VT* Md = Mst + (0 * COLS + lc0) * 32 + lane;      // this warp's state rows, one per direction
     VT* Ml = Mst + (1 * COLS + lc0) * 32 + lane;
@@ -176,16 +172,18 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
                       const VT* Snext, VT* Srow) {
         uint32_t Cr[NR], Sr[NR], L[NR], M[NR];
         unpack<NR>(cq[j], Cr);
-        if (SMODE == S_ACCUM) unpack<NR>(sq[j], Sr);
-        // next row's operands (on the last row Cnext / Snext point at the current row again: an unconditional
-        // load goes straight into cq / sq, a predicated one costs a dependent move that waits for it)
+        // S to accumulate onto: asked for now, needed after the three path steps; the row was pulled into L2 one
+        // row ago (a register prefetch of S like cq's does not fit the 64-register budget of 1024 threads)
+        VT sin;
+        if (SMODE == S_ACCUM) sin = Srow[j * 32];
+        // next row's C (on the last row Cnext points at the current row again: an unconditional load goes
+        // straight into cq, a predicated one costs a dependent move that waits for it)
         cq[j] = __ldg(Cnext + j * 32);
-        if (SMODE == S_ACCUM) sq[j] = Snext[j * 32];
         unpack<NR>(Md[j * 32], M);                               // (x, y-sy)
         path_step<NR>(M, Cr, L, P1p, P2p, lane);
         Md[j * 32] = pack<NR>(M);
 #pragma unroll
-        for (int r = 0; r < NR; r++) { Sr[r] = (SMODE == S_ACCUM) ? Sr[r] + L[r] : L[r]; M[r] = inl[r]; }
+        for (int r = 0; r < NR; r++) { Sr[r] = L[r]; M[r] = inl[r]; }
         path_step<NR>(M, Cr, L, P1p, P2p, lane);                 // (x-1, y-sy)
         Ml[j * 32] = pack<NR>(M);
 #pragma unroll
@@ -194,6 +192,12 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         Mr[j * 32] = pack<NR>(M);
 #pragma unroll
         for (int r = 0; r < NR; r++) Sr[r] += L[r];
+        if (SMODE == S_ACCUM) {
+            uint32_t Si[NR];
+            unpack<NR>(sin, Si);
+#pragma unroll
+            for (int r = 0; r < NR; r++) Sr[r] += Si[r];
+        }
         Srow[j * 32] = pack<NR>(Sr);
     };
     const uint32_t zeros[NR] = {};
@@ -206,6 +210,8 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
         const VT* Snext = S + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
         const uint32_t phase = (i >> 1) & 1;
+        if (SMODE == S_ACCUM && lane == 0 && nv > 0)      // next row's S segment of this warp -> L2 (one bulk prefetch)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Snext - lane), "r"((uint32_t)(nv * 32 * sizeof(VT))) : "memory");
         if (has_right) st_async(to_r + par * PARSTRIDE * (uint32_t)sizeof(VT), Ml[(CPW - 1) * 32], to_r_bar + par * V3_NW * 8);
         if (has_left) st_async(to_l + par * PARSTRIDE * (uint32_t)sizeof(VT), Mr[0], to_l_bar + par * V3_NW * 8);
         if (lane == 0 && rx_bytes) mbar_expect_tx(my_bar + par * V3_NW, rx_bytes);
@@ -342,13 +348,18 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
     const int wpb = 8;
     dim3 block(wpb * 32);
     dim3 gv((W1 + wpb - 1) / wpb, batch);
+    // Order of the chain (integer sums, so any order gives the same S): the left-to-right row kernel first, in
+    // WRITE mode -- it is HBM-bound and now moves two volumes instead of three -- then the vertical sweeps
+    // accumulate onto S (they are ALU-bound and have the bandwidth), then right-to-left fused with WTA.
+    int rc = v3d_launch_path_lr(ctx, batch, st);
+    if (rc) return rc;
     {
         V3dScope scope(ctx, ST_PATHS, st);
         // top-down sweep: predecessors (x, y-1), (x-1, y-1), (x+1, y-1)
-        int fused = try_vert3<NR>(ctx, batch, +1, false, st);
+        int fused = try_vert3<NR>(ctx, batch, +1, true, st);
         if (fused < 0) return fused;
         if (!fused) {
-            k_path_vert<NR, S_WRITE, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, +1, P1p, P2p);
+            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, +1, P1p, P2p);
             k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, +1, +1, P1p, P2p);
             k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, -1, +1, P1p, P2p);
             V3D_LAUNCHED(ctx, 3);
@@ -365,7 +376,7 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
             }
         }
     }
-    return v3d_launch_paths_horizontal(ctx, batch, st);
+    return v3d_launch_path_rl_wta(ctx, batch, st);
 }
 
 }  // namespace

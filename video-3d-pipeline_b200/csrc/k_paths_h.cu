@@ -15,7 +15,9 @@ constexpr int HW_WARPS = 8;   // warps (rows) per block
 constexpr int CH = 8;         // pixel steps per staged chunk
 
 // ------------------------------------------------------------------------------------------
-// left -> right (predecessor x-1):  S += L
+// left -> right (predecessor x-1):  S = L.  This is the FIRST path kernel of the chain: it only streams C in
+// and S out (two volume passes), so the HBM-bound row kernel carries no read-modify-write; the vertical sweep,
+// which is ALU-bound and has HBM bandwidth to spare, accumulates onto S instead.
 // ------------------------------------------------------------------------------------------
 template <int NR>
 __global__ void __launch_bounds__(HW_WARPS * 32)
@@ -45,9 +47,8 @@ k_path_lr_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1
         const int st = c % NST;
         const int x0 = c * CH;
         const uint32_t bytes = (uint32_t)min(CH, W1 - x0) * STEP_B;
-        mbar_expect_tx(&bars[wib][st], 2 * bytes);
+        mbar_expect_tx(&bars[wib][st], bytes);
         bulk_g2s(cst + st * CH * STEP_B, Cg + (size_t)x0 * STEP_B, bytes, &bars[wib][st]);
-        bulk_g2s(sst + st * CH * STEP_B, Sg + (size_t)x0 * STEP_B, bytes, &bars[wib][st]);
     };
     if (lane == 0) {
         issue(0);
@@ -65,23 +66,17 @@ k_path_lr_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1
         if (n == CH) {
 #pragma unroll
             for (int j = 0; j < CH; j++) {
-                uint32_t Cr[NR], Sr[NR], L[NR];
+                uint32_t Cr[NR], L[NR];
                 unpack<NR>(cs[j * 32], Cr);
-                unpack<NR>(ss[j * 32], Sr);
                 path_step<NR>(M, Cr, L, P1p, P2p, lane);
-#pragma unroll
-                for (int r = 0; r < NR; r++) Sr[r] += L[r];
-                ss[j * 32] = pack<NR>(Sr);
+                ss[j * 32] = pack<NR>(L);
             }
         } else {
             for (int j = 0; j < n; j++) {
-                uint32_t Cr[NR], Sr[NR], L[NR];
+                uint32_t Cr[NR], L[NR];
                 unpack<NR>(cs[j * 32], Cr);
-                unpack<NR>(ss[j * 32], Sr);
                 path_step<NR>(M, Cr, L, P1p, P2p, lane);
-#pragma unroll
-                for (int r = 0; r < NR; r++) Sr[r] += L[r];
-                ss[j * 32] = pack<NR>(Sr);
+                ss[j * 32] = pack<NR>(L);
             }
         }
         fence_async_smem();          // generic-proxy writes of every lane -> visible to the bulk store
@@ -252,7 +247,21 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, ui
 }
 
 template <int NR>
-int launch_h(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
+int launch_lr(v3d_ctx* ctx, int batch, cudaStream_t st)
+{
+    const int rows = batch * ctx->H;
+    const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
+    const size_t smem = (size_t)HW_WARPS * 2 * 3 * CH * 128 * NR;
+    dim3 grid((rows + HW_WARPS - 1) / HW_WARPS), block(HW_WARPS * 32);
+    V3D_CUDA(cudaFuncSetAttribute(k_path_lr_tma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    V3dScope scope(ctx, ST_LR, st);
+    k_path_lr_tma<NR><<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->W1, rows, P1p, P2p);
+    V3D_LAUNCHED(ctx, 1);
+    return V3D_OK;
+}
+
+template <int NR>
+int launch_wta(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
 {
     const int rows = batch * ctx->H;
     const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
@@ -261,30 +270,34 @@ int launch_h(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
     const bool pad = ctx->D != ctx->Dk;
     auto wta = tap_s ? (pad ? k_path_rl_wta_tma<NR, true, true> : k_path_rl_wta_tma<NR, true, false>)
                      : (pad ? k_path_rl_wta_tma<NR, false, true> : k_path_rl_wta_tma<NR, false, false>);
-    V3D_CUDA(cudaFuncSetAttribute(k_path_lr_tma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     V3D_CUDA(cudaFuncSetAttribute(wta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        V3dScope scope(ctx, ST_LR, st);
-        k_path_lr_tma<NR><<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->W1, rows, P1p, P2p);
-        V3D_LAUNCHED(ctx, 1);
-    }
-    {
-        V3dScope scope(ctx, ST_WTA, st);
-        wta<<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->rec, ctx->W1, rows, P1p, P2p, ctx->uniq, ctx->D);
-        V3D_LAUNCHED(ctx, 1);
-    }
+    V3dScope scope(ctx, ST_WTA, st);
+    wta<<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->rec, ctx->W1, rows, P1p, P2p, ctx->uniq, ctx->D);
+    V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
 
 }  // namespace
 
-int v3d_launch_paths_horizontal(v3d_ctx* ctx, int batch, cudaStream_t st)
+// first path kernel: S = L(left -> right)
+int v3d_launch_path_lr(v3d_ctx* ctx, int batch, cudaStream_t st)
+{
+    switch (ctx->Dk) {
+        case 64: return launch_lr<1>(ctx, batch, st);
+        case 128: return launch_lr<2>(ctx, batch, st);
+        case 256: return launch_lr<4>(ctx, batch, st);
+    }
+    return v3d_fail(V3D_EINVAL, "numDisparities %d unsupported (64, 128, 256)", ctx->D);
+}
+
+// last path kernel: right -> left fused with winner-takes-all
+int v3d_launch_path_rl_wta(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     const bool tap_s = ctx->debug_taps != 0;   // parity tests ask the WTA pass to also store S_total
     switch (ctx->Dk) {
-        case 64: return launch_h<1>(ctx, batch, st, tap_s);
-        case 128: return launch_h<2>(ctx, batch, st, tap_s);
-        case 256: return launch_h<4>(ctx, batch, st, tap_s);
+        case 64: return launch_wta<1>(ctx, batch, st, tap_s);
+        case 128: return launch_wta<2>(ctx, batch, st, tap_s);
+        case 256: return launch_wta<4>(ctx, batch, st, tap_s);
     }
     return v3d_fail(V3D_EINVAL, "numDisparities %d unsupported (64, 128, 256)", ctx->D);
 }

@@ -84,7 +84,8 @@ int v3d_launch_prefilter(v3d_ctx* ctx, const uint8_t* left, const uint8_t* right
 int v3d_launch_cost(v3d_ctx* ctx, int batch, cudaStream_t st);
 // k_paths.cu
 int v3d_launch_paths(v3d_ctx* ctx, int batch, cudaStream_t st);
-int v3d_launch_paths_horizontal(v3d_ctx* ctx, int batch, cudaStream_t st);
+int v3d_launch_path_lr(v3d_ctx* ctx, int batch, cudaStream_t st);
+int v3d_launch_path_rl_wta(v3d_ctx* ctx, int batch, cudaStream_t st);
 // k_post.cu
 int v3d_launch_select(v3d_ctx* ctx, int batch, cudaStream_t st);
 int v3d_launch_median(v3d_ctx* ctx, int batch, int16_t* dst, size_t dpitch, size_t dstride, cudaStream_t st);
