@@ -172,10 +172,6 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
                       const VT* Snext, VT* Srow) {
         uint32_t Cr[NR], Sr[NR], L[NR], M[NR];
         unpack<NR>(cq[j], Cr);
-        // S to accumulate onto: asked for now, needed after the three path steps; the row was pulled into L2 one
-        // row ago (a register prefetch of S like cq's does not fit the 64-register budget of 1024 threads)
-        VT sin;
-        if (SMODE == S_ACCUM) sin = Srow[j * 32];
         // next row's C (on the last row Cnext points at the current row again: an unconditional load goes
         // straight into cq, a predicated one costs a dependent move that waits for it)
         cq[j] = __ldg(Cnext + j * 32);
@@ -193,12 +189,20 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
 #pragma unroll
         for (int r = 0; r < NR; r++) Sr[r] += L[r];
         if (SMODE == S_ACCUM) {
-            uint32_t Si[NR];
-            unpack<NR>(sin, Si);
+            // S += (the three L): reduction performed by the L2 (RED, no return value), so the sweep neither
+            // loads S nor waits for it.  Packed 16-bit sums never carry (S_total < 2^16 by construction), so
+            // wide integer adds are exact.
+            if (NR == 1) {
+                atomicAdd(reinterpret_cast<unsigned int*>(Srow + j * 32), Sr[0]);
+            } else {
+                unsigned long long* sp = reinterpret_cast<unsigned long long*>(Srow + j * 32);
 #pragma unroll
-            for (int r = 0; r < NR; r++) Sr[r] += Si[r];
+                for (int r = 0; r < NR; r += 2)
+                    atomicAdd(sp + r / 2, (unsigned long long)Sr[r] | ((unsigned long long)Sr[r + (NR > 1 ? 1 : 0)] << 32));
+            }
+        } else {
+            Srow[j * 32] = pack<NR>(Sr);
         }
-        Srow[j * 32] = pack<NR>(Sr);
     };
     const uint32_t zeros[NR] = {};
     for (int i = 0; i < H; i++) {
@@ -210,8 +214,6 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
         const VT* Snext = S + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
         const uint32_t phase = (i >> 1) & 1;
-        if (SMODE == S_ACCUM && lane == 0 && nv > 0)      // next row's S segment of this warp -> L2 (one bulk prefetch)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(Snext - lane), "r"((uint32_t)(nv * 32 * sizeof(VT))) : "memory");
         if (has_right) st_async(to_r + par * PARSTRIDE * (uint32_t)sizeof(VT), Ml[(CPW - 1) * 32], to_r_bar + par * V3_NW * 8);
         if (has_left) st_async(to_l + par * PARSTRIDE * (uint32_t)sizeof(VT), Mr[0], to_l_bar + par * V3_NW * 8);
         if (lane == 0 && rx_bytes) mbar_expect_tx(my_bar + par * V3_NW, rx_bytes);
