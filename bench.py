@@ -50,12 +50,12 @@ CELLS = W1 * EYE_H * D
 ALG_IOPS = (31 + 9 * 5) * CELLS                          # 18.8 Gop
 # DRAM bytes per frame measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 15-frame launch / 15), see profiles/README.md; keyed by bench stage.
-NCU_DRAM_BYTES_PER_FRAME = {      # profiles/r01b_ncu_full_top6.csv
-    "cost": (1.981027e9 + 7.375259e9) / 15,
-    "vertical": (7.431941e9 + 7.386773e9) / 15,
-    "lr": (14.863835e9 + 7.394008e9) / 15,
-    "wta": (14.863620e9 + 0.237158e9) / 15,
-    "guided": (0.451309e9 + 1.939497e9 + 2.407548e9 + 0.245043e9) / 2 / 15,
+NCU_DRAM_BYTES_PER_FRAME = {      # profiles/r01c_ncu_full_top6.csv
+    "cost": (1.978932e9 + 7.377900e9) / 15,
+    "vertical": (14.864149e9 + 7.384173e9) / 15,
+    "lr": (7.431806e9 + 7.390104e9) / 15,
+    "wta": (14.863663e9 + 0.236377e9) / 15,
+    "guided": (0.451155e9 + 1.938307e9 + 2.408194e9 + 0.244270e9) / 2 / 15,
 }
 
 
@@ -350,8 +350,8 @@ def run_ours(args):
         vol = 2.0 * CELLS                 # one uint16 cost volume, bytes per frame
         kernels = {   # stage -> (kernel name, launches in the stage, design bytes per frame)
             "cost": ("k_cost", 1, vol + 0.15e9),
-            "vertical": ("k_path_vert3", 1, 2 * vol),
-            "lr": ("k_path_lr_tma", 1, 3 * vol),
+            "vertical": ("k_path_vert3", 1, 3 * vol),      # C read + S read-modify-write (L2 reductions)
+            "lr": ("k_path_lr_tma", 1, 2 * vol),
             "wta": ("k_path_rl_wta_tma", 1, 2 * vol),
             "guided": ("k_guided_coeff_s + k_guided_apply_s (avg of 2)", 2, (GUIDE_BYTES + 16 * GW * GH) / 2 + GW * GH * 9.0),
         }
@@ -419,8 +419,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0,
-                    help="frames per step per GPU (default: lanes x the co-resident clusters of the fused sweep, 75 on most B200s)")
-    ap.add_argument("--lanes", type=int, default=5, help="streams/contexts the batch is split over")
+                    help="frames per step per GPU (default: lanes x the co-resident clusters of the fused sweep, 90 on most B200s)")
+    ap.add_argument("--lanes", type=int, default=6, help="streams/contexts the batch is split over")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
