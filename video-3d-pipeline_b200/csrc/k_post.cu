@@ -105,8 +105,9 @@ k_median3(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t dpi
 
 // ---------------------------------------------------------------------------------------------
 // Speckle filter = connected components (4-neighbour, edge iff both valid and |a-b| <= maxDiff)
-// with a size threshold.  Lock-free union-find on pixel indices; component size counted at the
-// root with warp-aggregated atomics.  Order independent, like cv2.filterSpeckles.
+// with a size threshold.  Lock-free union-find on pixel indices; sizes are kept per horizontal RUN (at the
+// run's first pixel) and added to the component's root once per run, so only run heads ever walk the
+// union-find forest.  Order independent, like cv2.filterSpeckles.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int uf_find(const int* L, int i)
 {
@@ -166,7 +167,21 @@ k_ccl_rows(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, 
         int pre = carry_s;
         for (int w = 0; w < wid; w++) pre = max(pre, wmax[w]);
         start = max(start, pre);
-        if (x < W) { L[rowbase + x] = rowbase + start; sizes[rowbase + x] = 0; }
+        if (x < W) L[rowbase + x] = rowbase + start;
+        // run length, accumulated at the run head (sizes[] was zeroed before the launch): one atomic per
+        // stretch of equal `start` inside a warp; invalid pixels are their own start and count nothing
+        {
+            const bool valid = x < W && d[x] != INV;
+            const int key = valid ? start : -2 - (int)threadIdx.x;
+            const int prev = __shfl_up_sync(V3D_FULL_MASK, key, 1);
+            const bool head = lane == 0 || key != prev;
+            const unsigned heads = __ballot_sync(V3D_FULL_MASK, head);
+            if (head && valid) {
+                const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
+                const int len = later ? __ffs(later) : 32 - lane;
+                atomicAdd(&sizes[rowbase + start], len);
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 255) carry_s = start;
         __syncthreads();
@@ -193,29 +208,18 @@ k_ccl_merge(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e,
     uf_union(L, i, i - W);
 }
 
+// Pass 3: every run head that is not its component's root adds its run length to the root (and is flattened
+// onto it).  sizes[i] != 0 exactly at run heads; nobody adds to a non-root, so reading it here is race free.
 __global__ void __launch_bounds__(256)
-k_ccl_count(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
-            int* __restrict__ sizes, int W, int H)
+k_ccl_count(int* __restrict__ L, int* __restrict__ sizes, int n_total)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    const bool in = x < W;
-    int root = -1;
-    if (in) {
-        const int v = disp[(size_t)b * dstride_e + (size_t)y * dpitch_e + x];
-        if (v != INV) {
-            const int i = (b * H + y) * W + x;
-            root = uf_find(L, i);
-            L[i] = root;                       // flatten (roots never change after the merge kernel)
-        }
-    }
-    // warp-aggregate by segments of equal root among the 32 consecutive pixels: one atomic per segment
-    const int lane = threadIdx.x & 31;
-    const int prev = __shfl_up_sync(V3D_FULL_MASK, root, 1);
-    const bool head = lane == 0 || root != prev;
-    const unsigned heads = __ballot_sync(V3D_FULL_MASK, head);
-    if (head && root >= 0) {
-        const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
-        const int len = later ? __ffs(later) : 32 - lane;     // distance to the next segment head
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const int len = sizes[i];
+    if (len == 0) return;
+    const int root = uf_find(L, i);
+    if (root != i) {
+        L[i] = root;                           // roots never change after the merge kernel
         atomicAdd(&sizes[root], len);
     }
 }
@@ -228,7 +232,7 @@ k_ccl_apply(int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, const
     if (x >= W) return;
     int16_t* p = disp + (size_t)b * dstride_e + (size_t)y * dpitch_e + x;
     if (*p == INV) return;
-    const int root = L[(b * H + y) * W + x];
+    const int root = L[L[(b * H + y) * W + x]];      // pixel -> run head -> root (heads were flattened by k_ccl_count)
     if (sizes[root] <= maxSize) *p = (int16_t)newVal;
 }
 
@@ -367,9 +371,11 @@ int v3d_launch_speckle(v3d_ctx* ctx, int batch, int16_t* disp, size_t dpitch, si
     const int W = ctx->W, H = ctx->H;
     const int maxDiff = 16 * ctx->p.speckleRange;
     dim3 grid((W + 255) / 256, H, batch);
+    const int n_total = batch * W * H;
+    V3D_CUDA(cudaMemsetAsync(ctx->sizes, 0, (size_t)n_total * sizeof(int), st));
     k_ccl_rows<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H, maxDiff);
     k_ccl_merge<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff);
-    k_ccl_count<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H);
+    k_ccl_count<<<(n_total + 255) / 256, 256, 0, st>>>(ctx->labels, ctx->sizes, n_total);
     k_ccl_apply<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H,
                                       ctx->p.speckleWindowSize, (ctx->p.minDisparity - 1) * 16);
     V3D_LAUNCHED(ctx, 4);
