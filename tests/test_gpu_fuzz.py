@@ -51,11 +51,12 @@ def test_random_shapes_and_parameters_match_cv2(seed):
     assert np.array_equal(got, ref), dict(D=D, mode=mode, W=W, H=H, kind=kind, **kw)
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", list(range(12)) + [56, 57, 70, 83])
 def test_random_guided_upscale_shapes(seed):
-    """Arbitrary (non-integer) scale factors, radii and eps.  At the configured eps = 1e-3 (and above) the
-    fp32 kernels stay within the north-star budget, |q - oracle| < 0.5 LSB16 and uint16 within 1.  The filter
-    gain grows like 1/sqrt(eps), so for eps = 1e-4 the fp32 budget is stated (and tested) as 2 LSB16."""
+    """Arbitrary (non-integer) scale factors, radii and eps (1e-4 .. 1e-2): the fp32 kernels stay within the
+    north-star budget, |q - oracle| < 0.5 LSB16 and uint16 within 1, for all of them -- the 3x3 systems are
+    solved by LDL^T, which keeps its accuracy when the colour channels are nearly collinear and eps is small
+    (the adjugate form this replaced lost up to 8 LSB16 at eps = 1e-4).  Measured: <= 0.05 LSB16."""
     from oracle import guided as og
     rng = np.random.default_rng(500 + seed)
     w, h = int(rng.integers(20, 160)), int(rng.integers(20, 120))
@@ -71,10 +72,9 @@ def test_random_guided_upscale_shapes(seed):
                                     torch.from_numpy(guide)[None].cuda(), r, eps, want_q=True)
         out, q = out[0].cpu().numpy().view(np.uint16), q[0].cpu().numpy()
     oq, ou = og.guided_upscale(depth, guide, r, eps)
-    lsb = 0.5 if eps >= 1e-3 else 2.0
     err = float(np.abs(q - oq).max()) * 65535
-    assert err < lsb, dict(w=w, h=h, gw=gw, gh=gh, r=r, eps=eps, err_lsb16=err)
-    assert np.abs(out.astype(np.int64) - ou.astype(np.int64)).max() <= (1 if eps >= 1e-3 else 2)
+    assert err < 0.5, dict(w=w, h=h, gw=gw, gh=gh, r=r, eps=eps, err_lsb16=err)
+    assert np.abs(out.astype(np.int64) - ou.astype(np.int64)).max() <= 1
 
 
 @pytest.mark.parametrize("seed", range(8))

@@ -24,7 +24,7 @@ def _stale():
     if not OUT.exists():
         return True
     t = OUT.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "v3d_internal.h", CSRC / "path_common.cuh", HERE.parent / "include" / "v3d.h", Path(__file__)]
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "v3d_internal.h", CSRC / "path_common.cuh", CSRC / "tma.cuh", HERE.parent / "include" / "v3d.h", Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 
 

@@ -292,15 +292,27 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
                 const float c0 = acc[4] * kn - mI0 * mp, c1 = acc[5] * kn - mI1 * mp, c2 = acc[6] * kn - mI2 * mp;
                 const float s00 = acc[7] * kkn - mI0 * mI0 + eps, s01 = acc[8] * kkn - mI0 * mI1, s02 = acc[9] * kkn - mI0 * mI2;
                 const float s11 = acc[10] * kkn - mI1 * mI1 + eps, s12 = acc[11] * kkn - mI1 * mI2, s22 = acc[12] * kkn - mI2 * mI2 + eps;
-                const float k00 = s11 * s22 - s12 * s12, k01 = s02 * s12 - s01 * s22, k02 = s01 * s12 - s02 * s11;
-                const float k11 = s00 * s22 - s02 * s02, k12 = s01 * s02 - s00 * s12, k22 = s00 * s11 - s01 * s01;
-                const float det = s00 * k00 + s01 * k01 + s02 * k02;
-                float rc;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(det));
-                const float idet = rc * fmaf(-det, rc, 2.0f);        // one Newton step: ~1 ulp
-                const float a0 = (k00 * c0 + k01 * c1 + k02 * c2) * idet;
-                const float a1 = (k01 * c0 + k11 * c1 + k12 * c2) * idet;
-                const float a2 = (k02 * c0 + k12 * c1 + k22 * c2) * idet;
+                // (Sigma + eps I) a = cov(I, p) by LDL^T: the matrix is symmetric positive definite (pivots >= eps)
+                // and for nearly collinear colour channels -- the usual case -- this stays accurate where the
+                // adjugate / determinant form loses digits like (lambda_max / eps)^2.  Reciprocals: approx + one
+                // Newton step (~1 ulp).
+                auto rcp = [](float x) -> float {
+                    float r;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+                    return r * fmaf(-x, r, 2.0f);
+                };
+                const float i0 = rcp(s00);
+                const float l1 = s01 * i0, l2 = s02 * i0;
+                const float d1 = fmaf(-l1, s01, s11), e1 = fmaf(-l1, s02, s12);
+                const float i1 = rcp(d1);
+                const float l21 = e1 * i1;
+                const float d2 = fmaf(-l21, e1, fmaf(-l2, s02, s22));
+                const float i2 = rcp(d2);
+                const float y1 = fmaf(-l1, c0, c1);
+                const float y2 = fmaf(-l21, y1, fmaf(-l2, c0, c2));
+                const float a2 = y2 * i2;
+                const float a1 = fmaf(-l21, a2, y1 * i1);
+                const float a0 = fmaf(-l2, a2, fmaf(-l1, a1, c0 * i0));
                 // b referred to a guide centred at 0.5:  q = a.(I - 0.5) + b
                 const float bb = (mp + cp) - a0 * (mI0 + cI0) - a1 * (mI1 + cI1) - a2 * (mI2 + cI2);
                 ab[orow + X] = make_float4(a0, a1, a2, bb);
