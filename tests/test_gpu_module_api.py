@@ -96,3 +96,10 @@ def test_process_video_sbs_and_upscale(tmp_path):
     assert len(pngs) == 3
     img = cv2.imread(str(pngs[0]), cv2.IMREAD_UNCHANGED)
     assert img.dtype == np.uint16 and img.shape == (2 * H, 4 * W)
+    # GPU-side PNG writer for the 4K frames: identical pixels
+    up0 = SimpleDepthUpscaler(use_nvenc=True, png_compression=0, preview=False)
+    up0.process_depth_upscaling(str(out_dir), str(gclip), output_path=str(tmp_path / "depth_4k_fast.mp4"))
+    fast = sorted((tmp_path / "depth_4k_fast_png16").glob("*.png"))
+    assert len(fast) == 3
+    for a, b in zip(pngs, fast):
+        assert np.array_equal(cv2.imread(str(a), cv2.IMREAD_UNCHANGED), cv2.imread(str(b), cv2.IMREAD_UNCHANGED))

@@ -25,12 +25,19 @@ class SimpleDepthUpscaler:
     """Depth upscaling to the 4K frame size (reference class: upscale.py:12)."""
 
     def __init__(self, use_nvenc: bool = True, radius: int = 8, eps: float = 1e-3, batch_size: int = 4,
-                 gpu_index: int = 0):
+                 gpu_index: int = 0, png_compression: int = 1, png_threads: int = 6, preview: bool = True,
+                 decode_threads: int = 4):
         self.use_nvenc = use_nvenc          # kept for signature compatibility (upscale.py:15-16)
         self.radius = int(radius)
         self.eps = float(eps)
         self.batch_size = int(batch_size)
         self.gpu_index = int(gpu_index)
+        # zlib level of the 16-bit 4K PNGs; 0 = stored blocks packed on the GPU (v3d_png16_pack): ~16.6 MB files,
+        # but no libpng / deflate on the host (cv2.imwrite of a 4K uint16 frame costs ~0.2 s of one core)
+        self.png_compression = int(png_compression)
+        self.png_threads = max(1, int(png_threads))
+        self.preview = bool(preview)        # also write the 8-bit mp4 preview at output_path
+        self.decode_threads = max(1, int(decode_threads))   # guide-video readers, each on a contiguous slice of the clip
         if not torch.cuda.is_available():
             raise RuntimeError("CUDA not available but requested")
         _native.lib()
@@ -65,56 +72,130 @@ class SimpleDepthUpscaler:
         png_dir = out_path.with_suffix("")
         png_dir = png_dir.parent / (png_dir.name + "_png16")
         png_dir.mkdir(parents=True, exist_ok=True)
-        writer = cv2.VideoWriter(str(out_path), cv2.VideoWriter_fourcc(*"mp4v"), float(fps),
-                                 (int(target_width), int(target_height)), False)
-        if not writer.isOpened():
-            writer = None
+        writer = None
+        if self.preview:
+            writer = cv2.VideoWriter(str(out_path), cv2.VideoWriter_fourcc(*"mp4v"), float(fps),
+                                     (int(target_width), int(target_height)), False)
+            if not writer.isOpened():
+                writer = None
 
-        cap = None
         if guide_video is not None:
-            cap = cv2.VideoCapture(str(guide_video))
-            if not cap.isOpened():
+            probe = cv2.VideoCapture(str(guide_video))
+            ok = probe.isOpened()
+            probe.release()
+            if not ok:
                 raise ValueError(f"Could not open video file: {guide_video}")
-            if guide_start_frame > 0:          # 4K frame of depth map 0 = audio alignment offset (align.py:65-76)
-                cap.set(cv2.CAP_PROP_POS_FRAMES, int(guide_start_frame))
         dev = torch.device("cuda", self.gpu_index)
-        pool = ThreadPoolExecutor(max_workers=4)
+        import queue
+        import threading
+        pool = ThreadPoolExecutor(max_workers=self.png_threads)
         pending = []
+        pinned = {}
+        gpu_png = self.png_compression == 0
+        png_args = [cv2.IMWRITE_PNG_COMPRESSION, self.png_compression]
+        n_batches = (len(depth_files) + self.batch_size - 1) // self.batch_size
+        # the preview video needs frames in order, so it keeps one reader; otherwise the clip is cut into
+        # contiguous slices, one reader (own VideoCapture, seeked to its first frame) each
+        n_readers = 1 if writer is not None else max(1, min(self.decode_threads, n_batches))
+        batches: "queue.Queue" = queue.Queue(maxsize=2 * n_readers + 1)
+
+        def read_depth(f):
+            d = cv2.imread(f, cv2.IMREAD_UNCHANGED)
+            if d is None or d.ndim != 2:
+                raise ValueError(f"Unreadable depth map: {f}")
+            return d.astype(np.uint16) if d.dtype == np.uint16 else (d.astype(np.uint16) * 257)
+
+        def producer(b0: int, b1: int):
+            # depth PNGs are read by the pool, the guide video is decoded sequentially: both overlap the GPU work
+            cap = None
+            try:
+                if guide_video is not None:
+                    cap = cv2.VideoCapture(str(guide_video))
+                    first = int(guide_start_frame) + b0 * self.batch_size   # 4K frame of depth map 0 = audio alignment offset (align.py:65-76)
+                    if first > 0:
+                        cap.set(cv2.CAP_PROP_POS_FRAMES, first)
+                for bi in range(b0, b1):
+                    s0 = bi * self.batch_size
+                    files = depth_files[s0:s0 + self.batch_size]
+                    maps = list(pool.map(read_depth, files))
+                    guides = []
+                    for d in maps:
+                        frame = None
+                        if cap is not None:
+                            ok, frame = cap.read()
+                            frame = frame if ok else None
+                        if frame is None:       # self-guided
+                            g8 = (cv2.resize(d, (target_width, target_height), interpolation=cv2.INTER_LINEAR) >> 8).astype(np.uint8)
+                            frame = np.repeat(g8[..., None], 3, axis=2)
+                        elif frame.shape[1] != target_width or frame.shape[0] != target_height:
+                            frame = cv2.resize(frame, (target_width, target_height), interpolation=cv2.INTER_AREA)
+                        guides.append(frame)                                    # BGR; swapped to RGB on the GPU
+                    batches.put((s0, maps, guides))
+            except BaseException as e:
+                batches.put(e)
+            finally:
+                if cap is not None:
+                    cap.release()
+                batches.put(None)
+
+        base, extra = divmod(n_batches, n_readers)
+        prods, at = [], 0
+        for k in range(n_readers):
+            nb = base + (1 if k < extra else 0)
+            prods.append(threading.Thread(target=producer, args=(at, at + nb), daemon=True))
+            at += nb
+        for t in prods:
+            t.start()
+        live = len(prods)
         try:
-            for s in range(0, len(depth_files), self.batch_size):
-                files = depth_files[s:s + self.batch_size]
-                maps = []
-                for f in files:
-                    d = cv2.imread(f, cv2.IMREAD_UNCHANGED)
-                    if d is None or d.ndim != 2:
-                        raise ValueError(f"Unreadable depth map: {f}")
-                    maps.append(d.astype(np.uint16) if d.dtype == np.uint16 else (d.astype(np.uint16) * 257))
-                guides = []
-                for d in maps:
-                    frame = None
-                    if cap is not None:
-                        ok, frame = cap.read()
-                        frame = frame if ok else None
-                    if frame is None:       # self-guided
-                        g8 = (cv2.resize(d, (target_width, target_height), interpolation=cv2.INTER_LINEAR) >> 8).astype(np.uint8)
-                        frame = np.repeat(g8[..., None], 3, axis=2)
-                    elif frame.shape[1] != target_width or frame.shape[0] != target_height:
-                        frame = cv2.resize(frame, (target_width, target_height), interpolation=cv2.INTER_AREA)
-                    guides.append(frame[..., ::-1])                         # BGR -> RGB guide
+            while live:
+                item = batches.get()
+                if item is None:
+                    live -= 1
+                    continue
+                if isinstance(item, BaseException):
+                    raise item
+                s0, maps, guides = item
                 ctx = self._context(target_width, target_height, len(maps))
+                n = len(maps)
+                if pinned.get("shape") != (self.batch_size, target_height, target_width):
+                    pinned["shape"] = (self.batch_size, target_height, target_width)
+                    pinned["g"] = torch.empty((self.batch_size, target_height, target_width, 3), dtype=torch.uint8).pin_memory()
+                g_h = pinned["g"][:n]
+                g_np = g_h.numpy()
+                for i, g in enumerate(guides):
+                    np.copyto(g_np[i], g)
                 d_t = torch.from_numpy(np.stack(maps).view(np.int16)).to(dev).view(torch.uint16)
-                g_t = torch.from_numpy(np.ascontiguousarray(np.stack(guides))).to(dev)
-                out = ctx.guided_upscale(d_t, g_t, self.radius, self.eps).cpu().numpy().view(np.uint16)
-                for i in range(len(maps)):
-                    pending.append(pool.submit(cv2.imwrite, str(png_dir / f"depth4k_{s + i:06d}.png"), out[i].copy()))
-                    if writer is not None:
-                        writer.write((out[i] >> 8).astype(np.uint8))
+                g_t = g_h.to(dev, non_blocking=True).flip(-1).contiguous()       # BGR -> RGB guide
+                out_dev = ctx.guided_upscale(d_t, g_t, self.radius, self.eps)
+                if gpu_png:
+                    pay = ctx.png16_pack(out_dev).cpu().numpy()                  # also orders the reuse of the pinned guide buffer
+                    for i in range(n):
+                        # the row view keeps `pay` alive until the file is written: no per-frame copy
+                        pending.append(pool.submit(_native.write_png16, str(png_dir / f"depth4k_{s0 + i:06d}.png"),
+                                                   memoryview(pay[i]), target_width, target_height))
+                    prev, out = None, None
+                    if writer is not None:     # high bytes for the 8-bit preview (torch has no uint16 shifts)
+                        prev = ((out_dev.view(torch.int16).to(torch.int32) & 0xFFFF) >> 8).to(torch.uint8).cpu().numpy()
+                else:
+                    prev = None
+                    out = out_dev.cpu().numpy().view(np.uint16)
+                    for i in range(n):
+                        pending.append(pool.submit(cv2.imwrite, str(png_dir / f"depth4k_{s0 + i:06d}.png"), out[i], png_args))
+                if writer is not None:
+                    for i in range(len(maps)):
+                        writer.write(prev[i] if prev is not None else (out[i] >> 8).astype(np.uint8))
             for f in pending:
                 f.result()
         finally:
+            while any(t.is_alive() for t in prods):     # unblock producers stuck on a full queue
+                try:
+                    batches.get_nowait()
+                except queue.Empty:
+                    pass
+                for t in prods:
+                    t.join(timeout=0.01)
             pool.shutdown(wait=True)
-            if cap is not None:
-                cap.release()
             if writer is not None:
                 writer.release()
         if not out_path.exists():          # no encoder in this OpenCV build: leave a pointer file
