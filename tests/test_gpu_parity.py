@@ -339,7 +339,7 @@ def test_two_lanes_from_two_host_threads():
 def test_fused_sweep_reports_clusters_and_matches_unfused_shapes():
     """Shapes one cluster's shared memory can hold take the cluster-fused sweep (8 CTAs for D <= 128,
     16 CTAs for D = 256); wider ones take the per-direction kernels.  Both must equal cv2."""
-    for (W, H, D, expect_fused) in ((400, 40, 128, True), (600, 30, 256, True), (2100, 6, 256, False),
+    for (W, H, D, expect_fused) in ((400, 40, 128, True), (600, 30, 256, True), (2100, 6, 256, True), (2300, 6, 256, False),
                                     (2200, 6, 128, False)):
         left, right, _ = synthetic.stereo_pair(8, 0, W, H, D)
         with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=1)) as ctx:

@@ -327,11 +327,16 @@ template <int NR>
 int try_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
 {
     if (ctx->no_fused_vertical) return 0;
-    constexpr int CL = NR <= 2 ? 8 : 16, NW = NR <= 2 ? 32 : 16;
+#ifndef V3D_V3_NW4
+#define V3D_V3_NW4 18
+#endif
+    constexpr int CL = NR <= 2 ? 8 : 16, NW = NR <= 2 ? 32 : V3D_V3_NW4;
     const int need = (ctx->W1 + CL * NW - 1) / (CL * NW);
     int rc;
     if (need <= 2) rc = launch_vert3<NR, 2, CL, NW>(ctx, batch, sy, accum, st);
     else if (need <= 4) rc = launch_vert3<NR, 4, CL, NW>(ctx, batch, sy, accum, st);
+    else if (need <= 5 && NR > 2) rc = launch_vert3<NR, (NR > 2 ? 5 : 7), CL, NW>(ctx, batch, sy, accum, st);
+    else if (need <= 6 && NR > 2) rc = launch_vert3<NR, (NR > 2 ? 6 : 7), CL, NW>(ctx, batch, sy, accum, st);
     else if (need <= 7) rc = launch_vert3<NR, 7, CL, NW>(ctx, batch, sy, accum, st);
     else if (need <= 8 && NR <= 2) rc = launch_vert3<NR, (NR <= 2 ? 8 : 7), CL, NW>(ctx, batch, sy, accum, st);
     else return 0;      // wider than one cluster's shared memory: per-direction kernels
