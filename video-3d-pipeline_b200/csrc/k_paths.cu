@@ -330,7 +330,10 @@ int try_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
 #ifndef V3D_V3_NW4
 #define V3D_V3_NW4 18
 #endif
-    constexpr int CL = NR <= 2 ? 8 : 16, NW = NR <= 2 ? 32 : V3D_V3_NW4;
+#ifndef V3D_V3_NW2
+#define V3D_V3_NW2 32
+#endif
+    constexpr int CL = NR <= 2 ? 8 : 16, NW = NR <= 2 ? V3D_V3_NW2 : V3D_V3_NW4;
     const int need = (ctx->W1 + CL * NW - 1) / (CL * NW);
     int rc;
     if (need <= 2) rc = launch_vert3<NR, 2, CL, NW>(ctx, batch, sy, accum, st);
