@@ -445,6 +445,10 @@ constexpr int SNT = 128, SR = 4, SGR = 8;
 #ifndef V3D_GUIDED_CGR
 #define V3D_GUIDED_CGR 8
 #endif
+#ifndef V3D_GUIDED_CNT
+#define V3D_GUIDED_CNT 128
+#endif
+constexpr int SNC = V3D_GUIDED_CNT;      // threads (= region columns) per CTA of the coefficient kernel
 constexpr int SGC = V3D_GUIDED_CGR;      // outputs per horizontal run of the coefficient kernel (4 spreads the pass over all four warps but costs more shared-memory traffic: measured slower)
 
 template <int RT>
@@ -459,20 +463,22 @@ int launch_guided_stream(v3d_ctx* ctx, const uint16_t* depth, int w, int h, cons
     int seg = (gh + segs - 1) / segs;
     seg = (seg + SR - 1) / SR * SR;
     segs = (gh + seg - 1) / seg;
-    const size_t sm_c = coeff_s_smem<RT, SNT, SR, SGC>(win);
+    const size_t sm_c = coeff_s_smem<RT, SNC, SR, SGC>(win);
     constexpr int SRA = 8;            // rows per group of the apply kernel
     const size_t sm_a = (size_t)SRA * row_pitch<RT, SNT, SGR>() * 16 + (size_t)(win + SRA) * SNT * 16;
     const size_t sm_a_max = (size_t)SRA * row_pitch<RT, SNT, SGR>() * 16 + (size_t)(2 * GRMAX + 1 + SRA) * SNT * 16;
     if (!(ctx->guided_attr_set & (1 << RT))) {
-        V3D_CUDA(cudaFuncSetAttribute(k_guided_coeff_s<RT, SNT, SR, SGC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)coeff_s_smem<RT, SNT, SR, SGC>(2 * GRMAX + 1)));
+        V3D_CUDA(cudaFuncSetAttribute(k_guided_coeff_s<RT, SNC, SR, SGC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)coeff_s_smem<RT, SNC, SR, SGC>(2 * GRMAX + 1)));
         V3D_CUDA(cudaFuncSetAttribute(k_guided_apply_s<RT, SNT, SRA, SGR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a_max));
         V3D_CUDA(cudaFuncSetAttribute(k_guided_apply_s<RT, SNT, SRA, SGR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a_max));
         ctx->guided_attr_set |= (1 << RT);
     }
     const bool vec = q == nullptr && (gw % 8 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)guide % 8 == 0);
     dim3 grid(strips, segs, batch);
-    k_guided_coeff_s<RT, SNT, SR, SGC><<<grid, SNT, sm_c, st>>>(depth, w, h, guide, gw, gh, r, eps, seg, ctx->ab);
+    const int TWC = (SNC - 2 * r) & ~7;
+    dim3 grid_c((gw + TWC - 1) / TWC, segs, batch);
+    k_guided_coeff_s<RT, SNC, SR, SGC><<<grid_c, SNC, sm_c, st>>>(depth, w, h, guide, gw, gh, r, eps, seg, ctx->ab);
     if (vec) k_guided_apply_s<RT, SNT, SRA, SGR, true><<<grid, SNT, sm_a, st>>>(ctx->ab, guide, gw, gh, r, seg, out, q);
     else k_guided_apply_s<RT, SNT, SRA, SGR, false><<<grid, SNT, sm_a, st>>>(ctx->ab, guide, gw, gh, r, seg, out, q);
     V3D_LAUNCHED(ctx, 2);
