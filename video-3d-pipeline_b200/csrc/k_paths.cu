@@ -6,8 +6,9 @@
 // One WARP owns one path (a row for the horizontal directions, a wrapped column/diagonal for the
 // vertical ones) and walks it sequentially.  Lane l holds the 2*NR consecutive disparities
 // d = 2*NR*l .. 2*NR*l + 2*NR-1 as NR packed int16x2 registers, so one warp-step is one coalesced
-// 128*NR-byte load of C, the DPX packed min/add recurrence, one CREDUX warp-min and one
-// read-modify-write of S.
+// 128*NR-byte load of C, the DPX packed min/add recurrence and one CREDUX warp-min.  S is written by the first
+// kernel of the chain (left-to-right rows), accumulated by the vertical sweeps (L2 reductions) and consumed by
+// the last one (right-to-left rows + winner-takes-all); sums of integers, so the order does not matter.
 //   state kept per path:  M[d] = min(L[d] - min_d L, P2)      (the P2 clamp folds the "minL + P2" term)
 //   step:                 L[d] = C[d] + min(M[d], min(M[d-1], M[d+1]) + P1)
 // A predecessor outside the window contributes L = 0, i.e. M = 0, which is also the initial state.
@@ -92,14 +93,15 @@ k_path_vert(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, 
 // The three directions of one vertical sweep fused: (x, y-sy), (x-1, y-sy), (x+1, y-sy).
 // One thread-block CLUSTER of V3_CL CTAs owns a whole frame; warp g of the cluster owns the CPW
 // consecutive columns [g*CPW, (g+1)*CPW) for every row and every direction, so C is read once and
-// S is written once per sweep instead of three reads of C and a write + two read-modify-writes of S.
+// S is touched once per sweep (a plain store in WRITE mode, RED.ADD in ACCUM mode) instead of three reads of C
+// and three read-modify-writes of S.
 // Path state M lives in shared memory ([dir][column][d]); a diagonal path moves to the neighbouring
 // column every row, so the only inter-warp traffic is one 2*NR*64-byte state vector per warp
 // boundary and direction per row.  Each warp PUSHES its two boundary vectors into its neighbours' inboxes
 // (st.async through distributed shared memory, completion counted on the receiver's mbarrier), so a warp
 // synchronises with its two neighbours only: no cluster-wide barrier, no memory fence, no remote loads.
 // ------------------------------------------------------------------------------------------
-// V3_CL CTAs per cluster, V3_NW warps per CTA: 8 x 32 for D <= 128 (portable cluster size); 16 x 16 for
+// V3_CL CTAs per cluster, V3_NW warps per CTA: 8 x 32 for D <= 128 (portable cluster size); 16 x 18 for
 // D = 256, whose 512-byte state vectors need the shared memory of 16 SMs per frame (non-portable size).
 
 template <int NR, int CPW, int SMODE, int V3_CL, int V3_NW>

@@ -2,9 +2,9 @@
 // One warp walks one image row.  A row of C (and of S) is a single contiguous run of
 // W1 * D * 2 bytes, so instead of one 128*NR-byte load per pixel step the warp's elected lane streams
 // it through shared memory in CH-pixel chunks with cp.async.bulk (SASS: UBLKCP) completing on an
-// mbarrier, NST chunks deep.  The left-to-right pass updates S in place in its shared-memory stage
-// and writes the chunk back with a bulk store; the right-to-left pass only reads (S_total feeds the
-// winner-takes-all directly and never returns to memory).
+// mbarrier, NST chunks deep.  The left-to-right pass (first kernel of the chain) writes L into its
+// shared-memory stage and sends the chunk to S with a bulk store; the right-to-left pass (last kernel)
+// only reads: S_total feeds the winner-takes-all directly and never returns to memory.
 // Replaces the per-row part of OpenCV computeDisparitySGBM (depth.py:341).  Spec: SURVEY.md A.3/A.4.
 #include "path_common.cuh"
 #include "tma.cuh"
