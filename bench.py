@@ -243,10 +243,13 @@ def run_ours(args):
             probe.depth_frames(z, False, want=())
             torch.cuda.synchronize(dev)
             Bl = probe.fused_sweep_clusters or 15
+        # lanes that fit: a lane holds ~1.45 GB per frame (cost volumes, guided coefficients, in/out buffers)
+        free_b, _total_b = torch.cuda.mem_get_info(dev)
+        n_lanes = max(1, min(n_lanes, int((free_b - 6e9) // (Bl * 1.45e9))))
         if world > 1:   # every rank must do the same amount of work (weak scaling): agree on the minimum
-            t = torch.tensor([Bl], dtype=torch.int64, device=dev)
+            t = torch.tensor([Bl, n_lanes], dtype=torch.int64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            Bl = int(t.item())
+            Bl, n_lanes = int(t[0].item()), int(t[1].item())
         B = Bl * n_lanes
     sbs_np, guide_np = synthetic_batch(Bl)
 
