@@ -228,6 +228,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # Host placement: pinned staging buffers on the GPU's NUMA node; with several ranks per box also keep the
+    # rank's (launch-and-copy only) host threads on that node's cores.  V3D_NUMA_BIND=0 switches both off.
+    from video_3d_pipeline import shard
+    numa = {"node": shard.prefer_gpu_numa_memory(local),
+            "cpus_bound": len(shard.bind_to_gpu_numa(local)) if world > 1 else 0}
+
     params = nv.SgbmParams(numDisparities=D, mode=nv.MODE_SGBM)
     n_lanes = max(1, args.lanes)
     if args.batch > 0:
@@ -384,6 +390,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             import cv2
+            shard.reset_numa_memory_policy()    # the CPU workers allocate wherever they run
             workers = max(1, min(host_cores(), 64))
             fps, dfps, wall = cpu_reference(1, workers)
             cpu = {"value": fps, "unit": UNIT, "cores": workers, "kind": "reference",
@@ -405,6 +412,7 @@ def run_ours(args):
             "workspace_gb": workspace_gb,
             "fused_sweep_clusters": fused_clusters,
             "lanes": n_lanes,
+            "host_numa": numa,
         }
     for lane in lanes:
         lane.ctx.close()

@@ -161,6 +161,29 @@ def test_frame_ranges_partition():
         frame_ranges(0, 10, 0)
 
 
+def test_numa_placement_helpers(monkeypatch):
+    """Host placement of shard workers: cpulist parsing, no-ops without topology, preferred-node policy."""
+    from video_3d_pipeline import shard
+    assert shard.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert shard.parse_cpulist("") == [] and shard.parse_cpulist("5") == [5]
+    before = os.sched_getaffinity(0)
+    # no GPU here: topology unknown -> nothing is changed
+    assert shard.gpu_local_cpus(0) == [] and shard.gpu_numa_node(0) == -1
+    assert shard.prefer_gpu_numa_memory(0) == -1 and shard.bind_to_gpu_numa(0) == []
+    # fewer local CPUs than the floor -> no binding either
+    monkeypatch.setattr(shard, "gpu_local_cpus", lambda i: sorted(before)[:1])
+    assert shard.bind_to_gpu_numa(0, min_cpus=2) == [] and os.sched_getaffinity(0) == before
+    # the switch
+    monkeypatch.setattr(shard, "gpu_numa_node", lambda i: 0)
+    monkeypatch.setenv("V3D_NUMA_BIND", "0")
+    assert shard.prefer_gpu_numa_memory(0) == -1
+    monkeypatch.delenv("V3D_NUMA_BIND")
+    try:
+        assert shard.prefer_gpu_numa_memory(0) in (0, -1)      # -1 where the sandbox forbids set_mempolicy
+    finally:
+        shard.reset_numa_memory_policy()
+
+
 _GLOO_SCRIPT = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1])
