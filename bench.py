@@ -345,6 +345,8 @@ def run_ours(args):
     stages = {k: v / prof_steps for k, v in ctx.stage_ms().items()}
     ctx.set_timing(False)
     workspace_gb = sum(l.ctx.workspace_bytes for l in lanes) / 1e9
+    # measured integer add/min rate of this GPU (register-only probe kernel, ~1 s): the ALU roofline's denominator
+    int_probe = nv.probe_int_throughput(local) if rank == 0 else None
     fused_clusters = ctx.fused_sweep_clusters
 
     line = None
@@ -384,7 +386,11 @@ def run_ours(args):
                                "design_gbs": v[2] * Bl / max(stages.get(k, 1e-9) / v[1] / 1000.0, 1e-12) / 1e9}
                            for k, v in kernels.items()},
             "alu": {"algorithmic_iops_per_frame": ALG_IOPS, "achieved_tiops": ALG_IOPS * (value / world) / 1e12,
-                    "nominal_peak_tiops": 148 * 128 * 1.965e9 / 1e12},
+                    "nominal_peak_tiops": 148 * 128 * 1.965e9 / 1e12,
+                    "measured": {k: {"lane_instr_tps": v[0] / 1e12, "algorithmic_tiops": v[1] / 1e12}
+                                 for k, v in int_probe.items()},
+                    "measured_peak_tiops": max(v[1] for v in int_probe.values()) / 1e12,
+                    "frac_of_measured_peak": ALG_IOPS * (value / world) / max(v[1] for v in int_probe.values())},
             "whole_step_hbm_frac_algorithmic": ALG_BYTES_FUSED * (value / world) / 1e9 / hbm_peak,
         }
         cpu = None

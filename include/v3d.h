@@ -191,6 +191,15 @@ int v3d_set_timing(v3d_ctx* ctx, int enabled);
 double v3d_stage_ms(v3d_ctx* ctx, int stage, const char** name);
 int v3d_reset_timing(v3d_ctx* ctx);
 
+/* Measurement aid, not on the data path (the ALU roofline's denominator is the MEASURED integer
+ * min/add rate of the device).  Runs a register-only kernel at full occupancy on `device` (synchronous,
+ * a few milliseconds) and reports the sustained rate of one instruction mix of the path recurrence:
+ *   kind 0  int32 add + min (one fused instruction);   kind 1  packed u16x2 add, then min (two);
+ *   kind 2  fused packed u16x2 add-min (one DPX instruction).
+ * lane_instr_per_s = thread-level instructions per second, algorithmic_ops_per_s = add/min operations
+ * on cost cells per second (a packed instruction handles two cells). */
+int v3d_probe_int_throughput(int device, int kind, double* lane_instr_per_s, double* algorithmic_ops_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,10 @@ def test_no_cpu_fallback():
     assert b"no CPU fallback" in _native.lib().v3d_last_error()
     with pytest.raises(RuntimeError):
         _native.Context(400, 20)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _native.probe_int_throughput(0)
+    a = C.c_double()
+    assert _native.lib().v3d_probe_int_throughput(0, 7, C.byref(a), C.byref(a)) == _native.V3D_EINVAL
     from video_3d_pipeline.depth import IGEVStereoDepthExtractor
     with pytest.raises(RuntimeError, match="CUDA not available"):
         IGEVStereoDepthExtractor(work_dir="/tmp/v3d_t", cache_dir="/tmp/v3d_t")

@@ -103,3 +103,21 @@ def test_process_video_sbs_and_upscale(tmp_path):
     assert len(fast) == 3
     for a, b in zip(pngs, fast):
         assert np.array_equal(cv2.imread(str(a), cv2.IMREAD_UNCHANGED), cv2.imread(str(b), cv2.IMREAD_UNCHANGED))
+
+
+def test_integer_throughput_probe_is_plausible():
+    """v3d_probe_int_throughput: the measured denominator of bench.py's ALU roofline."""
+    import torch
+    from video_3d_pipeline import _native as nv
+    r = nv.probe_int_throughput(0)
+    assert set(r) == {"int32_add_min", "u16x2_add_then_min", "u16x2_fused_add_min"}
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for name, (instr, ops) in r.items():
+        # between 8 and 128 lanes per SM and clock at 1-2.2 GHz
+        assert 8 * sms * 1.0e9 < instr < 128 * sms * 2.2e9, (name, instr)
+        assert ops >= instr
+    # measured on B200: the fused add-min (VIADDMNMX) issues at 64 lanes per SM and clock whether packed or not,
+    # the VIADD + VIMNMX.U16x2 pair at ~113 (two pipes) -- so per cell the packed forms tie and both double int32
+    assert r["u16x2_fused_add_min"][1] > 0.8 * r["u16x2_add_then_min"][1]
+    assert r["u16x2_fused_add_min"][1] > 1.5 * r["int32_add_min"][1]
+    assert r["u16x2_add_then_min"][0] > 1.5 * r["u16x2_fused_add_min"][0]

@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "video_3d_pipeline" / "libv3d.so"
-SOURCES = ["v3d_api.cu", "k_gray.cu", "k_cost.cu", "k_paths.cu", "k_paths_h.cu", "k_post.cu", "k_guided.cu", "k_png.cu"]
+SOURCES = ["v3d_api.cu", "k_gray.cu", "k_cost.cu", "k_paths.cu", "k_paths_h.cu", "k_post.cu", "k_guided.cu", "k_png.cu", "k_probe.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--shared",

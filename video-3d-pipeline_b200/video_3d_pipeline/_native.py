@@ -76,6 +76,8 @@ def lib():
     L.v3d_reset_timing.argtypes = [vp]
     L.v3d_stage_ms.argtypes = [vp, i32, C.POINTER(C.c_char_p)]
     L.v3d_stage_ms.restype = C.c_double
+    L.v3d_probe_int_throughput.argtypes = [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.v3d_probe_int_throughput.restype = i32
     for name in ("v3d_create", "v3d_destroy", "v3d_split_gray", "v3d_bgr_to_gray", "v3d_unsqueeze_bgr",
                  "v3d_sgbm_compute", "v3d_set_debug_taps", "v3d_debug_tap", "v3d_debug_tap_copy", "v3d_postprocess", "v3d_normalize_u16",
                  "v3d_guided_upscale", "v3d_depth_frames", "v3d_depth_frames_host", "v3d_set_depth_scale", "v3d_png16_pack", "v3d_set_timing",
@@ -83,6 +85,17 @@ def lib():
         getattr(L, name).restype = i32
     _lib = L
     return L
+
+
+def probe_int_throughput(device=0):
+    """Measured integer add/min rates of `device` (v3d_probe_int_throughput): {mix: (lane-instructions/s,
+    algorithmic cell operations/s)} for the three instruction mixes of the path recurrence."""
+    out = {}
+    for kind, name in enumerate(("int32_add_min", "u16x2_add_then_min", "u16x2_fused_add_min")):
+        a, b = C.c_double(), C.c_double()
+        _check(lib().v3d_probe_int_throughput(device, kind, C.byref(a), C.byref(b)), "v3d_probe_int_throughput")
+        out[name] = (a.value, b.value)
+    return out
 
 
 def _raise(rc, what):
