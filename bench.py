@@ -50,12 +50,12 @@ CELLS = W1 * EYE_H * D
 ALG_IOPS = (31 + 9 * 5) * CELLS                          # 18.8 Gop
 # DRAM bytes per frame measured by `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 15-frame launch / 15), see profiles/README.md; keyed by bench stage.
-NCU_DRAM_BYTES_PER_FRAME = {      # profiles/r01c_ncu_full_top6.csv
-    "cost": (1.978932e9 + 7.377900e9) / 15,
-    "vertical": (14.864149e9 + 7.384173e9) / 15,
-    "lr": (7.431806e9 + 7.390104e9) / 15,
-    "wta": (14.863663e9 + 0.236377e9) / 15,
-    "guided": (0.451155e9 + 1.938307e9 + 2.408194e9 + 0.244270e9) / 2 / 15,
+NCU_DRAM_BYTES_PER_FRAME = {      # profiles/r01d_ncu_full_top6.csv
+    "cost": (1.978912e9 + 7.377555e9) / 15,
+    "vertical": (14.863622e9 + 7.381563e9) / 15,
+    "lr": (7.432424e9 + 7.389744e9) / 15,
+    "wta": (14.864874e9 + 0.236329e9) / 15,
+    "guided": (0.452217e9 + 1.937375e9 + 2.407501e9 + 0.245115e9) / 2 / 15,
 }
 
 
