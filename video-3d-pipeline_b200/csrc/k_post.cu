@@ -103,6 +103,62 @@ k_median3(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t dpi
     dst[(size_t)b * dstride_e + (size_t)y * dpitch_e + x] = (int16_t)v[4];
 }
 
+// The same median on 8 pixels per thread: 128-bit loads and stores, the exchange network on packed
+// int16 pairs (two pixels per VIMNMX.S16x2).  Needs W % 8 == 0 and 16-byte aligned rows on both sides.
+__device__ __forceinline__ void cswap2(uint32_t& a, uint32_t& b)
+{
+    const uint32_t t = __vmins2(a, b);
+    b = __vmaxs2(a, b);
+    a = t;
+}
+
+__global__ void __launch_bounds__(256)
+k_median3_v8(const int16_t* __restrict__ src, int16_t* __restrict__ dst, size_t dpitch_e, size_t dstride_e, int W, int H,
+             int n_groups)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups) return;
+    const int gpr = W >> 3;                          // groups per row
+    const int row = t / gpr, x0 = (t - row * gpr) << 3;
+    const int b = row / H, y = row - b * H;
+    const int16_t* img = src + (size_t)b * W * H;
+    uint32_t v[4][9];                                // [pixel pair][3 rows x (left, centre, right)]
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+        const int16_t* r = img + (size_t)min(max(y + dy, 0), H - 1) * W;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(r + x0));
+        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+        const uint32_t lw = (uint32_t)(uint16_t)__ldg(r + max(x0 - 1, 0)) << 16;      // left neighbour in the high half
+        const uint32_t rw = (uint32_t)(uint16_t)__ldg(r + min(x0 + 8, W - 1));        // right neighbour in the low half
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            v[k][(dy + 1) * 3 + 0] = __byte_perm(k ? w[k - 1] : lw, w[k], 0x5432);   // (p[x-1], p[x])
+            v[k][(dy + 1) * 3 + 1] = w[k];                                            // (p[x],   p[x+1])
+            v[k][(dy + 1) * 3 + 2] = __byte_perm(w[k], k < 3 ? w[k + 1] : rw, 0x5432); // (p[x+1], p[x+2])
+        }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t (&a)[9] = v[k];
+        cswap2(a[1], a[2]); cswap2(a[4], a[5]); cswap2(a[7], a[8]);
+        cswap2(a[0], a[1]); cswap2(a[3], a[4]); cswap2(a[6], a[7]);
+        cswap2(a[1], a[2]); cswap2(a[4], a[5]); cswap2(a[7], a[8]);
+        cswap2(a[0], a[3]); cswap2(a[5], a[8]); cswap2(a[4], a[7]);
+        cswap2(a[3], a[6]); cswap2(a[1], a[4]); cswap2(a[2], a[5]);
+        cswap2(a[4], a[7]); cswap2(a[4], a[2]); cswap2(a[6], a[4]);
+        cswap2(a[4], a[2]);
+        o[k] = a[4];
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)b * dstride_e + (size_t)y * dpitch_e + x0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// true when 8-pixel (16-byte) vector accesses are legal on an int16 image with these pitches
+__host__ inline bool vec8_ok(const void* p, size_t pitch_e, size_t stride_e, int W)
+{
+    return (W & 7) == 0 && (pitch_e & 7) == 0 && (stride_e & 7) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Speckle filter = connected components (4-neighbour, edge iff both valid and |a-b| <= maxDiff)
 // with a size threshold.  Lock-free union-find on pixel indices; sizes are kept per horizontal RUN (at the
@@ -208,6 +264,36 @@ k_ccl_merge(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e,
     uf_union(L, i, i - W);
 }
 
+// The same pass on 8 pixels per thread (128-bit loads of both rows; the left neighbours of a pixel are the
+// previous loop iteration's values).
+__global__ void __launch_bounds__(256)
+k_ccl_merge_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
+               int W, int H, int maxDiff, int n_groups)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups) return;
+    const int gpr = W >> 3;
+    const int row = t / gpr, x0 = (t - row * gpr) << 3;
+    const int b = row / H, y = row - b * H;
+    if (y == 0) return;
+    const int16_t* r1 = disp + (size_t)b * dstride_e + (size_t)y * dpitch_e + x0;
+    const int16_t* r0 = r1 - dpitch_e;
+    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(r1)), q0 = __ldg(reinterpret_cast<const uint4*>(r0));
+    const uint32_t w1[4] = { q1.x, q1.y, q1.z, q1.w }, w0[4] = { q0.x, q0.y, q0.z, q0.w };
+    bool has_left = x0 > 0;
+    int vl = has_left ? (int)__ldg(r1 - 1) : INV, ul = has_left ? (int)__ldg(r0 - 1) : INV;
+    const int base = row * W + x0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int v = (int16_t)(w1[i >> 1] >> ((i & 1) * 16)), u = (int16_t)(w0[i >> 1] >> ((i & 1) * 16));
+        if (ccl_edge(v, u, maxDiff)) {
+            const bool covered = has_left && ccl_edge(v, vl, maxDiff) && ccl_edge(u, ul, maxDiff) && ccl_edge(vl, ul, maxDiff);
+            if (!covered) uf_union(L, base + i, base + i - W);
+        }
+        vl = v; ul = u; has_left = true;
+    }
+}
+
 // Pass 3: every run head that is not its component's root adds its run length to the root (and is flattened
 // onto it).  sizes[i] != 0 exactly at run heads; nobody adds to a non-root, so reading it here is race free.
 __global__ void __launch_bounds__(256)
@@ -234,6 +320,44 @@ k_ccl_apply(int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, const
     if (*p == INV) return;
     const int root = L[L[(b * H + y) * W + x]];      // pixel -> run head -> root (heads were flattened by k_ccl_count)
     if (sizes[root] <= maxSize) *p = (int16_t)newVal;
+}
+
+// 8 pixels per thread; pixels of one horizontal run share their label, so the two dependent look-ups
+// (run head -> root, root -> size) happen once per run instead of once per pixel.
+__global__ void __launch_bounds__(256)
+k_ccl_apply_v8(int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, const int* __restrict__ L,
+               const int* __restrict__ sizes, int W, int H, int maxSize, int newVal, int n_groups)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups) return;
+    const int gpr = W >> 3;
+    const int row = t / gpr, x0 = (t - row * gpr) << 3;
+    const int b = row / H, y = row - b * H;
+    uint4* p = reinterpret_cast<uint4*>(disp + (size_t)b * dstride_e + (size_t)y * dpitch_e + x0);
+    const uint4 q = *p;
+    uint32_t w[4] = { q.x, q.y, q.z, q.w };
+    const uint32_t inv2 = ((uint32_t)(uint16_t)INV << 16) | (uint16_t)INV;
+    if (q.x == inv2 && q.y == inv2 && q.z == inv2 && q.w == inv2) return;
+    const int4* lp = reinterpret_cast<const int4*>(L + (size_t)row * W + x0);      // row * W + x0 is a multiple of 8
+    const int4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
+    const int lab[8] = { l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w };
+    int prev = -1;
+    bool kill = false, changed = false;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int16_t v = (int16_t)(w[i >> 1] >> ((i & 1) * 16));
+        if (v == INV) continue;
+        if (lab[i] != prev) {
+            prev = lab[i];
+            kill = sizes[L[prev]] <= maxSize;      // run head -> root (flattened by k_ccl_count) -> component size
+        }
+        if (kill) {
+            w[i >> 1] = (i & 1) ? (w[i >> 1] & 0x0000ffffu) | ((uint32_t)(uint16_t)newVal << 16)
+                                : (w[i >> 1] & 0xffff0000u) | (uint16_t)newVal;
+            changed = true;
+        }
+    }
+    if (changed) *p = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -289,6 +413,71 @@ k_epilogue(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, 
         }
         u16[(size_t)b * n + i] = o;
     }
+}
+
+// 8 pixels per thread (128-bit loads); max(disp, 0) and the running min / max on packed int16 pairs.
+__global__ void __launch_bounds__(256)
+k_minmax_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int W, int H, int* __restrict__ mm)
+{
+    const int b = blockIdx.y;
+    const int16_t* d = disp + (size_t)b * dstride_e;
+    const int gpr = W >> 3, n_groups = gpr * H;
+    uint32_t lo = 0x7fff7fffu, hi = 0u;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_groups; t += gridDim.x * blockDim.x) {
+        const int y = t / gpr, x0 = (t - y * gpr) << 3;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(d + (size_t)y * dpitch_e + x0));
+        const uint32_t a = __vmaxs2(q.x, 0u), c = __vmaxs2(q.y, 0u), e = __vmaxs2(q.z, 0u), g = __vmaxs2(q.w, 0u);
+        lo = __vminu2(lo, __vminu2(__vminu2(a, c), __vminu2(e, g)));      // non-negative from here: unsigned order
+        hi = __vmaxu2(hi, __vmaxu2(__vmaxu2(a, c), __vmaxu2(e, g)));
+    }
+    int l = (int)min(lo & 0xffffu, lo >> 16), h = (int)max(hi & 0xffffu, hi >> 16);
+    if (lo == 0x7fff7fffu && hi == 0u) { l = 0x7fffffff; h = -0x7fffffff; }     // this thread saw no pixel
+    l = __reduce_min_sync(V3D_FULL_MASK, l);
+    h = __reduce_max_sync(V3D_FULL_MASK, h);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[2 * b], l); atomicMax(&mm[2 * b + 1], h); }
+}
+
+__global__ void __launch_bounds__(256)
+k_epilogue_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int W, int H,
+              const int* __restrict__ mm, float* __restrict__ f32, uint16_t* __restrict__ u16, int fixed, float lo, float hi)
+{
+    const int b = blockIdx.y;
+    const int gpr = W >> 3;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= gpr * H) return;
+    const int y = t / gpr, x0 = (t - y * gpr) << 3;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(disp + (size_t)b * dstride_e + (size_t)y * dpitch_e + x0));
+    const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int v = max((int)(int16_t)(w[i >> 1] >> ((i & 1) * 16)), 0);
+        f[i] = __fdiv_rn((float)v, 16.0f);
+    }
+    const size_t o = (size_t)b * W * H + (size_t)y * W + x0;       // dense outputs; a multiple of 8
+    if (f32) {
+        float4* fp = reinterpret_cast<float4*>(f32 + o);
+        fp[0] = make_float4(f[0], f[1], f[2], f[3]);
+        fp[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    if (!u16) return;
+    uint32_t r[8];
+    if (fixed) {             // opt-in clip-level scale (v3d_set_depth_scale)
+        const float den = __fsub_rn(hi, lo);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float tt = __fdiv_rn(__fsub_rn(f[i], lo), den);
+            r[i] = (uint16_t)__fmul_rn(fminf(fmaxf(tt, 0.0f), 1.0f), 65535.0f);
+        }
+    } else {
+        const float mn = __fdiv_rn((float)mm[2 * b], 16.0f), mx = __fdiv_rn((float)mm[2 * b + 1], 16.0f);
+        const float den = __fsub_rn(mx, mn);
+#pragma unroll
+        for (int i = 0; i < 8; i++)     // three separately rounded IEEE operations, like numpy (depth.py:401)
+            r[i] = mx > mn ? (uint32_t)(uint16_t)__fmul_rn(__fdiv_rn(__fsub_rn(f[i], mn), den), 65535.0f) : 0u;
+    }
+    *reinterpret_cast<uint4*>(u16 + o) = make_uint4(r[0] | (r[1] << 16), r[2] | (r[3] << 16), r[4] | (r[5] << 16),
+                                                    r[6] | (r[7] << 16));
 }
 
 // save_depth_map on an arbitrary float map (depth.py:397-403): per-frame min/max then the same three
@@ -358,8 +547,13 @@ int v3d_launch_select(v3d_ctx* ctx, int batch, cudaStream_t st)
 int v3d_launch_median(v3d_ctx* ctx, int batch, int16_t* dst, size_t dpitch, size_t dstride, cudaStream_t st)
 {
     V3dScope scope(ctx, ST_MEDIAN, st);
-    dim3 grid((ctx->W + 255) / 256, ctx->H, batch);
-    k_median3<<<grid, 256, 0, st>>>(ctx->raw, dst, dpitch / 2, dstride / 2, ctx->W, ctx->H);
+    if (vec8_ok(dst, dpitch / 2, dstride / 2, ctx->W)) {
+        const int n_groups = batch * ctx->H * (ctx->W / 8);
+        k_median3_v8<<<(n_groups + 255) / 256, 256, 0, st>>>(ctx->raw, dst, dpitch / 2, dstride / 2, ctx->W, ctx->H, n_groups);
+    } else {
+        dim3 grid((ctx->W + 255) / 256, ctx->H, batch);
+        k_median3<<<grid, 256, 0, st>>>(ctx->raw, dst, dpitch / 2, dstride / 2, ctx->W, ctx->H);
+    }
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
@@ -374,10 +568,18 @@ int v3d_launch_speckle(v3d_ctx* ctx, int batch, int16_t* disp, size_t dpitch, si
     const int n_total = batch * W * H;
     V3D_CUDA(cudaMemsetAsync(ctx->sizes, 0, (size_t)n_total * sizeof(int), st));
     k_ccl_rows<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H, maxDiff);
-    k_ccl_merge<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff);
+    const bool vec = vec8_ok(disp, dpitch / 2, dstride / 2, W);
+    const int n_groups = vec ? batch * H * (W / 8) : 0;
+    if (vec) k_ccl_merge_v8<<<(n_groups + 255) / 256, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff, n_groups);
+    else k_ccl_merge<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff);
     k_ccl_count<<<(n_total + 255) / 256, 256, 0, st>>>(ctx->labels, ctx->sizes, n_total);
-    k_ccl_apply<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H,
-                                      ctx->p.speckleWindowSize, (ctx->p.minDisparity - 1) * 16);
+    if (vec) {
+        k_ccl_apply_v8<<<(n_groups + 255) / 256, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H,
+                                                               ctx->p.speckleWindowSize, (ctx->p.minDisparity - 1) * 16, n_groups);
+    } else {
+        k_ccl_apply<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H,
+                                          ctx->p.speckleWindowSize, (ctx->p.minDisparity - 1) * 16);
+    }
     V3D_LAUNCHED(ctx, 4);
     return V3D_OK;
 }
@@ -387,15 +589,24 @@ int v3d_launch_post(v3d_ctx* ctx, const int16_t* disp, size_t dpitch, size_t dst
 {
     V3dScope scope(ctx, ST_POST, st);
     const int W = ctx->W, H = ctx->H, n = W * H;
+    const bool vec = vec8_ok(disp, dpitch / 2, dstride / 2, W) && (!f32 || (reinterpret_cast<uintptr_t>(f32) & 15) == 0) &&
+                     (!u16 || (reinterpret_cast<uintptr_t>(u16) & 15) == 0);
     if (u16 && !ctx->fixed_scale) {
         k_minmax_init<<<(batch + 255) / 256, 256, 0, st>>>(ctx->minmax, batch);
         dim3 g(148 * 2, batch);
-        k_minmax<<<g, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax);
+        if (vec) k_minmax_v8<<<g, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax);
+        else k_minmax<<<g, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax);
         V3D_LAUNCHED(ctx, 2);
     }
-    dim3 grid((n + 255) / 256, batch);
-    k_epilogue<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax, f32, u16, ctx->fixed_scale,
-                                     ctx->scale_lo, ctx->scale_hi);
+    if (vec) {
+        dim3 grid((n / 8 + 255) / 256, batch);
+        k_epilogue_v8<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax, f32, u16, ctx->fixed_scale,
+                                            ctx->scale_lo, ctx->scale_hi);
+    } else {
+        dim3 grid((n + 255) / 256, batch);
+        k_epilogue<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, W, H, ctx->minmax, f32, u16, ctx->fixed_scale,
+                                         ctx->scale_lo, ctx->scale_hi);
+    }
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
