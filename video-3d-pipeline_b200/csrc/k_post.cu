@@ -244,6 +244,83 @@ k_ccl_rows(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, 
     }
 }
 
+// Pass 1 on 8 pixels per thread (W % 8 == 0, W <= 2048: the whole row in one step, one block scan instead of
+// one per 256 pixels).  Threads whose 8 pixels lie in one run aggregate their length over the warp (one atomic
+// per stretch of such threads); the others add their own stretches.
+__global__ void __launch_bounds__(256)
+k_ccl_rows_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
+              int* __restrict__ sizes, int W, int H, int maxDiff)
+{
+    __shared__ int wmax[8];
+    const int y = blockIdx.x % H, b = blockIdx.x / H;
+    const int16_t* d = disp + (size_t)b * dstride_e + (size_t)y * dpitch_e;
+    const int rowbase = (b * H + y) * W;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x0 = threadIdx.x * 8;
+    const bool act = x0 < W;
+    int v[8], st[8];
+    int cur = -1;                                    // -1: still inside the run that entered from the left
+    if (act) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(d + x0));
+        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+        int pl = x0 > 0 ? (int)__ldg(d + x0 - 1) : INV;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            v[i] = (int16_t)(w[i >> 1] >> ((i & 1) * 16));
+            if (!ccl_edge(v[i], pl, maxDiff)) cur = x0 + i;      // a run (or an invalid pixel) starts here
+            st[i] = cur;
+            pl = v[i];
+        }
+    }
+    // exclusive max-scan of every thread's last start over the block
+    int incl = cur;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(V3D_FULL_MASK, incl, o);
+        if (lane >= o) incl = max(incl, t);
+    }
+    if (lane == 31) wmax[wid] = incl;
+    int pre = __shfl_up_sync(V3D_FULL_MASK, incl, 1);
+    if (lane == 0) pre = -1;
+    __syncthreads();
+    for (int w = 0; w < wid; w++) pre = max(pre, wmax[w]);
+    bool uniform = act;                              // all 8 pixels valid and in one run
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (st[i] < 0) st[i] = pre;
+            uniform = uniform && v[i] != INV && st[i] == st[0];
+        }
+        int4* lp = reinterpret_cast<int4*>(L + rowbase + x0);
+        lp[0] = make_int4(rowbase + st[0], rowbase + st[1], rowbase + st[2], rowbase + st[3]);
+        lp[1] = make_int4(rowbase + st[4], rowbase + st[5], rowbase + st[6], rowbase + st[7]);
+    }
+    // run lengths, accumulated at the run heads (sizes[] was zeroed before the launch)
+    const int key = uniform ? st[0] : -2 - (int)threadIdx.x;
+    const int prev = __shfl_up_sync(V3D_FULL_MASK, key, 1);
+    const bool head = lane == 0 || key != prev;
+    const unsigned heads = __ballot_sync(V3D_FULL_MASK, head);
+    if (uniform) {
+        if (head) {
+            const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
+            const int cnt = later ? __ffs(later) : 32 - lane;
+            atomicAdd(&sizes[rowbase + st[0]], 8 * cnt);
+        }
+    } else if (act) {
+        int s = -1, len = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (v[i] == INV) continue;
+            if (st[i] != s) {
+                if (len) atomicAdd(&sizes[rowbase + s], len);
+                s = st[i]; len = 0;
+            }
+            len++;
+        }
+        if (len) atomicAdd(&sizes[rowbase + s], len);
+    }
+}
+
 // Pass 2: vertical unions.  A union is skipped when the pixel's left neighbour already carries it
 // (x-1,y)~(x,y), (x-1,y-1)~(x,y-1) and (x-1,y)~(x-1,y-1) all hold.
 __global__ void __launch_bounds__(256)
@@ -567,8 +644,9 @@ int v3d_launch_speckle(v3d_ctx* ctx, int batch, int16_t* disp, size_t dpitch, si
     dim3 grid((W + 255) / 256, H, batch);
     const int n_total = batch * W * H;
     V3D_CUDA(cudaMemsetAsync(ctx->sizes, 0, (size_t)n_total * sizeof(int), st));
-    k_ccl_rows<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H, maxDiff);
     const bool vec = vec8_ok(disp, dpitch / 2, dstride / 2, W);
+    if (vec && W <= 2048) k_ccl_rows_v8<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H, maxDiff);
+    else k_ccl_rows<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H, maxDiff);
     const int n_groups = vec ? batch * H * (W / 8) : 0;
     if (vec) k_ccl_merge_v8<<<(n_groups + 255) / 256, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff, n_groups);
     else k_ccl_merge<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff);
