@@ -18,8 +18,8 @@
  *     owns only the opaque context and its workspace.
  *   - Every call takes the cudaStream_t to run on (as void*; 0 = legacy default
  *     stream; pass torch.cuda.current_stream().cuda_stream) and is stream-ordered
- *     with no internal synchronisation, except the *_host entry points, which
- *     synchronise the stream before returning.
+ *     with no internal synchronisation, except v3d_depth_frames_host and
+ *     v3d_host_wait, which wait (sleeping, not spinning) for the outputs.
  *   - A context belongs to one device and one host thread at a time.
  *   - There is NO CPU fallback: without a CUDA device every compute entry point
  *     fails with V3D_ECUDA.
@@ -153,11 +153,40 @@ int v3d_depth_frames(v3d_ctx* ctx, const uint8_t* sbs_bgr, size_t sbs_pitch, siz
 
 /* Same path from HOST buffers (dense arrays; pinned memory recommended): copies
  * the inputs host->device, runs, copies the requested outputs device->host and
- * synchronises the stream.  This is the call the end-to-end numbers time. */
+ * waits for them (v3d_depth_frames_host_async + v3d_host_wait below).  This pair is
+ * the call the end-to-end numbers time. */
 int v3d_depth_frames_host(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, int h, int batch,
                           int unsqueeze, int16_t* disp_host, float* depth_f32_host,
                           uint16_t* depth_u16_host, const uint8_t* guide_rgb_host, int gw, int gh,
                           int r, float eps, uint16_t* out_4k_host, void* stream);
+
+/* Asynchronous form of v3d_depth_frames_host (replaces the batch loop body of depth.py:448-461 for a
+ * caller that keeps several batches in flight): enqueues the uploads -- one copy per frame on the
+ * context's upload stream, SBS frames first so that the SGBM chain runs under the guide upload -- the
+ * kernels on `stream`, and the downloads (one copy per frame, on the context's download stream), then
+ * returns without waiting.  `stream` finally waits for the downloads, so the call is stream-ordered as a
+ * whole.  The host buffers must stay valid, and the context must not be used by another host call, until
+ * v3d_host_wait(ctx) has returned.  v3d_depth_frames_host = this + v3d_host_wait. */
+int v3d_depth_frames_host_async(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, int h, int batch,
+                                int unsqueeze, int16_t* disp_host, float* depth_f32_host,
+                                uint16_t* depth_u16_host, const uint8_t* guide_rgb_host, int gw, int gh,
+                                int r, float eps, uint16_t* out_4k_host, void* stream);
+/* The upscale step alone from HOST buffers (replaces upscale.py:47-59 for one batch): depth_u16_host
+ * [batch][eye_h][eye_w] (the context's eye size) + guide_rgb_host [batch][gh][gw][3] -> out_u16_host
+ * [batch][gh][gw].  Asynchronous like the call above. */
+int v3d_guided_upscale_host_async(v3d_ctx* ctx, const uint16_t* depth_u16_host, const uint8_t* guide_rgb_host,
+                                  int gw, int gh, int batch, int r, float eps, uint16_t* out_u16_host,
+                                  void* stream);
+/* Block the calling host thread until the context's last *_host_async call has delivered its outputs.
+ * The wait sleeps on a blocking-sync CUDA event (no spinning), so one submit thread can drive many
+ * contexts and many ranks can share few host cores. */
+int v3d_host_wait(v3d_ctx* ctx);
+/* Measurement aid: exactly the host<->device copies of v3d_depth_frames_host_async (same streams, same
+ * per-frame granularity, same event dependencies) with NO kernel in between -- the ceiling the host side
+ * of a box puts on the end-to-end number.  disp_host / out_4k_host receive whatever the workspace holds. */
+int v3d_host_copy_only_async(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, int h, int batch,
+                             int16_t* disp_host, const uint8_t* guide_rgb_host, int gw, int gh,
+                             uint16_t* out_4k_host, void* stream);
 
 /* How many frames the fused vertical sweep keeps co-resident on this device (one thread-block
  * cluster per frame); batches that are a multiple of it leave no partial wave.  0 until the first

@@ -131,6 +131,46 @@ def test_cache_key_is_the_references(tmp_path):
     assert ex.is_cached(p, 2) and not ex.is_cached(p, 3)
     ex.depth_scale, ex.num_disparities = "fixed", 64     # opt-in output format gets its own cache entry
     assert ex.get_cache_path("clip.mkv", 5, 100) != p
+    # every knob that changes the pixels gets its own entry; reference-equivalent settings keep the reference hash
+    ex.depth_scale = "frame"
+    assert ex.get_cache_path("clip.mkv", 5, 100) == p
+    seen = {p}
+    for nd, mode, ign in ((128, 0, False), (64, 1, False), (128, 1, False), (64, 0, True)):
+        ex.num_disparities, ex.sgbm_mode, ex._guidance_ignored = nd, mode, ign
+        q = ex.get_cache_path("clip.mkv", 5, 100)
+        assert q not in seen
+        seen.add(q)
+
+
+def test_reader_plan_and_exact_seek_detection(tmp_path):
+    """Several decode threads only where a seek is frame-exact (intra-only codecs); slices are whole batches,
+    contiguous, and cover the range exactly once."""
+    import cv2
+    from video_3d_pipeline.depth import HybridStereoDepthExtractor as E
+    for first, count, bs, readers in ((0, 100, 8, 4), (10, 37, 8, 4), (3, 5, 8, 4), (0, 64, 8, 3), (0, 1, 1, 9)):
+        sl = E.plan_reader_slices(first, count, bs, readers, 1000)
+        assert len(sl) <= readers and sum(n for _, n, _ in sl) == count
+        at = first
+        for s0, n, idx in sl:
+            assert s0 == at and idx == 1000 + (s0 - first) and n > 0
+            assert (s0 - first) % bs == 0          # every slice starts on a batch boundary
+            at += n
+    frames = [np.full((32, 64, 3), 20 * i, np.uint8) for i in range(6)]
+
+    def write(path, fourcc):
+        vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*fourcc), 24.0, (64, 32))
+        if not vw.isOpened():
+            return False
+        for f in frames:
+            vw.write(f)
+        vw.release()
+        return path.exists() and path.stat().st_size > 0
+
+    if write(tmp_path / "intra.avi", "MJPG"):
+        assert E.seek_is_frame_exact(str(tmp_path / "intra.avi"))
+    if write(tmp_path / "gop.mp4", "mp4v"):
+        assert not E.seek_is_frame_exact(str(tmp_path / "gop.mp4"))      # long-GOP: one sequential reader
+    assert not E.seek_is_frame_exact(str(tmp_path / "missing.mkv"))
 
 
 def test_video_info_fallback_and_work_dir(tmp_path):
@@ -225,14 +265,40 @@ def test_two_rank_gloo_sharding(tmp_path):
     assert "GLOO_OK" in out.stdout
 
 
-def test_bench_reference_arm_schema():
-    """`bench.py --impl reference` contract fields (run at a tiny size through its helpers)."""
+def test_bench_configs_and_reference_arm_schema():
+    """bench.py: every BASELINE.json configuration carries SURVEY 8(d)'s algorithmic figures, and both arms print
+    the same `config` object for a configuration whatever the lane / batch choice (the driver compares it)."""
     sys.path.insert(0, str(ROOT))
     import bench
-    cfg = bench.workload_config(8, 2)
-    assert "workload" in cfg and cfg["global_frames_per_step"] == 16
-    assert bench.ALG_BYTES_DEPTH == 16588800 and bench.ALG_BYTES_FUSED == 53913600   # SURVEY 8(d)
-    assert bench.ALG_IOPS == 76 * 1792 * 1080 * 128
+    assert sorted(bench.CONFIGS) == ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"]
+    c = bench.CONFIGS
+    assert c["cfg1"].alg_bytes == 8294400 and c["cfg2"].alg_bytes == 16588800               # SURVEY 8(d)
+    assert c["cfg3"].alg_bytes == 49766400 and c["cfg4"].alg_bytes == c["cfg5"].alg_bytes == 53913600
+    assert c["cfg1"].alg_iops == 76 * 896 * 1080 * 64 and c["cfg2"].alg_iops == 76 * 1792 * 1080 * 128
+    assert c["cfg5"].alg_iops == 103 * 1664 * 1080 * 256
+    assert c["cfg4"].h2d == 12441600 + 24883200 and c["cfg4"].d2h == 16588800
+    for name, cfg in c.items():
+        a, b = bench.workload_config(cfg, 1), bench.workload_config(cfg, 1)
+        assert a == b and a["name"] == name and "workload" in a
+        assert not any(k in a for k in ("lanes", "frames_per_step_per_gpu", "global_frames_per_step"))
+
+
+def test_bench_reference_arm_runs_a_small_config(monkeypatch, capsys):
+    """`bench.py --impl reference` end to end on a shrunken configuration: one JSON line with the contract keys."""
+    import json
+    sys.path.insert(0, str(ROOT))
+    import bench
+    small = bench.Cfg("cfg4", 160, 48, 64, 0, True, True, bench.CONFIGS["cfg4"].workload)
+    monkeypatch.setitem(bench.CONFIGS, "cfg4", small)
+    monkeypatch.setattr(bench, "host_cores", lambda: 1)
+    monkeypatch.setenv("RANK", "0")
+    args = type("A", (), dict(config="cfg4", warmup=0, steps=1, gpus=1))()
+    assert bench.run_reference_arm(args) == 0
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["config"] == bench.workload_config(small, 1)
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
 
 
 def test_alignment_offset_semantics(tmp_path):

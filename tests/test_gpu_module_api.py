@@ -1,5 +1,7 @@
 """The reference-facing module API (video_3d_pipeline.depth / .upscale) on a GPU box, read like
 the tests the reference never had: same calls, same shapes, same values as the cv2 path."""
+from pathlib import Path
+
 import cv2
 import numpy as np
 import pytest
@@ -121,3 +123,151 @@ def test_integer_throughput_probe_is_plausible():
     assert r["u16x2_fused_add_min"][1] > 0.8 * r["u16x2_add_then_min"][1]
     assert r["u16x2_fused_add_min"][1] > 1.5 * r["int32_add_min"][1]
     assert r["u16x2_add_then_min"][0] > 1.5 * r["u16x2_fused_add_min"][0]
+
+
+def _decode_all(path):
+    cap = cv2.VideoCapture(str(path))
+    out = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        out.append(f)
+    cap.release()
+    return out
+
+
+def test_upscale_module_pixels_with_alignment_offset(tmp_path):
+    """process_depth_upscaling (upscale.py:75-123 surface) on a GPU box, pixel values checked: depth map i is
+    guided by DECODED 4K frame start + i, start = the audio-alignment offset stored next to the depth cache
+    (utils.py:299-327), BGR -> RGB on the GPU; output within 1 LSB of oracle.guided on exactly those inputs."""
+    import json
+    from oracle import guided as og
+    from video_3d_pipeline.upscale import SimpleDepthUpscaler
+    w, h, n, start = 160, 90, 3, 2
+    work = tmp_path / "work"
+    ddir = work / "depth_abc"
+    ddir.mkdir(parents=True)
+    maps = [synthetic.depth_u16(31, t, w, h) for t in range(n)]
+    for i, d in enumerate(maps):
+        assert cv2.imwrite(str(ddir / f"depth_{i:06d}.png"), d)
+    gclip = tmp_path / "uhd.avi"
+    _write_clip(gclip, [synthetic.guide_frame(31, t, 2 * w, 2 * h)[..., ::-1].copy() for t in range(n + start + 1)], fps=24.0)
+    decoded = _decode_all(gclip)                                  # what the upscaler's reader sees (MJPG is lossy)
+    assert len(decoded) == n + start + 1
+    (work / "alignment_data.json").write_text(json.dumps({"video1_path": "sbs.mkv", "video2_path": str(gclip),
+                                                          "time_offset_seconds": start / 24.0}))
+    for kw in (dict(), dict(png_compression=0, preview=False)):   # cv2 PNGs + preview / GPU-packed PNGs, several readers
+        out = tmp_path / ("o%d.mp4" % len(kw))
+        res = SimpleDepthUpscaler(use_nvenc=True, batch_size=2, **kw).process_depth_upscaling(str(ddir), str(gclip), output_path=str(out))
+        assert isinstance(res, str) and Path(res).exists()
+        pngs = sorted((tmp_path / (out.stem + "_png16")).glob("depth4k_*.png"))
+        assert len(pngs) == n
+        for i, p in enumerate(pngs):
+            got = cv2.imread(str(p), cv2.IMREAD_UNCHANGED)
+            assert got.dtype == np.uint16 and got.shape == (2 * h, 2 * w)
+            _, want = og.guided_upscale(maps[i], decoded[start + i][..., ::-1], 8, 1e-3)
+            assert np.abs(got.astype(np.int64) - want.astype(np.int64)).max() <= 1, (kw, i)
+            _, wrong = og.guided_upscale(maps[i], decoded[i][..., ::-1], 8, 1e-3)     # the offset matters
+            assert np.abs(got.astype(np.int64) - wrong.astype(np.int64)).max() > 1
+        # a second call finds the finished PNG sequence (upscale.py:104-107), not a placeholder file
+        again = SimpleDepthUpscaler(use_nvenc=True, batch_size=2, **kw).process_depth_upscaling(str(ddir), str(gclip), output_path=str(out))
+        assert again == res
+        if kw:
+            assert not out.exists() and Path(res).is_dir()        # preview=False: no fake .mp4
+
+
+def _run_pipeline_calls(sbs_video, video_4k, work_dir, max_frames):
+    """The calls run_pipeline.py makes with --skip-alignment, restated with its keyword arguments
+    (run_pipeline.py:63-68 constructor, :70-75 process_video_sbs, :92-98 upscale)."""
+    from video_3d_pipeline.depth import IGEVStereoDepthExtractor          # run_pipeline.py:12
+    from video_3d_pipeline.upscale import SimpleDepthUpscaler              # run_pipeline.py:13
+    extractor = IGEVStereoDepthExtractor(work_dir=work_dir, cache_dir=work_dir, unsqueeze_sbs=True, batch_size=8)
+    depth_dir = extractor.process_video_sbs(video_path=sbs_video, start_frame=0, max_frames=max_frames, force_reprocess=False)
+    upscaler = SimpleDepthUpscaler(use_nvenc=True)
+    video = upscaler.process_depth_upscaling(depth_dir=str(depth_dir), video_4k_path=video_4k,
+                                             output_path=f"{work_dir}/depth_4k_final.mp4", force_reprocess=False)
+    return depth_dir, video
+
+
+def _check_pipeline_outputs(work, sbs_clip, n):
+    m = cv2_chain.make_matcher(64, 0)                                     # depth.py:315-325 literals
+    decoded = _decode_all(sbs_clip)
+    dirs = [d for d in Path(work).glob("depth_*") if d.is_dir() and not d.name.endswith("_png16")]
+    assert len(dirs) == 1
+    for i in range(n):
+        got = cv2.imread(str(dirs[0] / f"depth_{i:06d}.png"), cv2.IMREAD_UNCHANGED)
+        ref = cv2_chain.normalize_u16(cv2_chain.depth_from_sbs(decoded[i], m, True))    # unsqueeze_sbs=True
+        assert got.dtype == np.uint16 and np.array_equal(got, ref), i
+    assert len(list((Path(work) / "depth_4k_final_png16").glob("depth4k_*.png"))) == n
+
+
+def test_run_pipeline_call_sequence_end_to_end(tmp_path):
+    """SURVEY section 2 row 7, "the drop-in test": what run_pipeline.py does with --skip-alignment --max-frames 4
+    on an MJPG clip pair, PNGs compared with the reference's cv2 chain on the decoded frames."""
+    sbs = tmp_path / "sbs.avi"
+    uhd = tmp_path / "uhd.avi"
+    _write_clip(sbs, [synthetic.sbs_frame(23, t, W // 2, H, 32) for t in range(6)])      # half-SBS 320x180, unsqueezed to 320/eye
+    _write_clip(uhd, [synthetic.guide_frame(23, t, 2 * W, 2 * H)[..., ::-1].copy() for t in range(6)])
+    work = tmp_path / "work"
+    _run_pipeline_calls(str(sbs), str(uhd), str(work), 4)
+    _check_pipeline_outputs(work, sbs, 4)
+
+
+def test_unmodified_reference_run_pipeline_if_present(tmp_path):
+    """INTEGRATION.md recipe A with the reference's own, unmodified run_pipeline.py: only where a checkout of the
+    reference exists next to a GPU (it does not travel to the GPU box: the test skips there, and the restated
+    call sequence above covers the same calls)."""
+    import os
+    import subprocess
+    import sys
+    ref = Path(os.environ.get("V3D_REFERENCE_DIR", "/root/reference"))
+    if not (ref / "run_pipeline.py").exists():
+        pytest.skip("no reference checkout on this box")
+    root = Path(__file__).resolve().parent.parent
+    shadow = tmp_path / "shadow"
+    (shadow / "src").mkdir(parents=True)
+    (shadow / "run_pipeline.py").symlink_to(ref / "run_pipeline.py")                      # unmodified: a symlink
+    (shadow / "src" / "video_3d_pipeline").symlink_to(root / "video-3d-pipeline_b200" / "video_3d_pipeline")
+    sbs, uhd = tmp_path / "sbs.avi", tmp_path / "uhd.avi"
+    _write_clip(sbs, [synthetic.sbs_frame(23, t, W // 2, H, 32) for t in range(6)])
+    _write_clip(uhd, [synthetic.guide_frame(23, t, 2 * W, 2 * H)[..., ::-1].copy() for t in range(6)])
+    work = tmp_path / "work"
+    r = subprocess.run([sys.executable, str(shadow / "run_pipeline.py"), str(sbs), str(uhd), "--work-dir", str(work),
+                        "--skip-alignment", "--max-frames", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _check_pipeline_outputs(work, sbs, 4)
+
+
+def test_long_gop_clip_reads_sequentially_and_matches_single_reader(tmp_path):
+    """seeking is not frame-exact on long-GOP streams, so such clips get ONE sequential reader whatever
+    decode_threads says; an intra-only clip split over several readers gives the same files as one reader."""
+    from video_3d_pipeline.depth import IGEVStereoDepthExtractor
+    frames = [synthetic.sbs_frame(24, t, W, H, D) for t in range(20)]
+    gop = tmp_path / "gop.mp4"
+    vw = cv2.VideoWriter(str(gop), cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (2 * W, H))
+    clips = []
+    if vw.isOpened():
+        for f in frames:
+            vw.write(f)
+        vw.release()
+        if gop.exists() and gop.stat().st_size > 0:
+            assert not IGEVStereoDepthExtractor.seek_is_frame_exact(str(gop))
+            clips.append(gop)
+    intra = tmp_path / "intra.avi"
+    _write_clip(intra, frames)
+    assert IGEVStereoDepthExtractor.seek_is_frame_exact(str(intra))
+    clips.append(intra)
+    for clip in clips:
+        outs = []
+        for k, threads in enumerate((1, 4)):
+            ex = IGEVStereoDepthExtractor(work_dir=str(tmp_path / f"w{clip.stem}{k}"), cache_dir=str(tmp_path / f"w{clip.stem}{k}"),
+                                          unsqueeze_sbs=False, batch_size=2, stereo_only=True, decode_threads=threads)
+            outs.append(ex.process_video_sbs(str(clip), start_frame=3, max_frames=15))
+        decoded = _decode_all(clip)
+        m = cv2_chain.make_matcher(D, 0)
+        for i in range(15):
+            a = cv2.imread(str(outs[0] / f"depth_{i:06d}.png"), cv2.IMREAD_UNCHANGED)
+            b = cv2.imread(str(outs[1] / f"depth_{i:06d}.png"), cv2.IMREAD_UNCHANGED)
+            assert np.array_equal(a, b), (clip.name, i)
+            assert np.array_equal(a, cv2_chain.normalize_u16(cv2_chain.depth_from_sbs(decoded[3 + i], m, False))), (clip.name, i)

@@ -346,3 +346,100 @@ def test_fused_sweep_reports_clusters_and_matches_unfused_shapes():
             d = ctx.sgbm_compute(torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda())[0].cpu().numpy()
             assert (ctx.fused_sweep_clusters > 0) == expect_fused
         assert np.array_equal(d, cv2_chain.make_matcher(D, 1).compute(left, right))
+
+
+def test_full_size_cfg5_vs_cv2():
+    """BASELINE configs[4] at full size, bit-exact against the reference's matcher: 1920x1080/eye, D=256,
+    MODE_HH (8 paths), speckle filter on (depth.py:315-325 with numDisparities / mode opened up, :341)."""
+    W, H, D = 1920, 1080, 256
+    frame = synthetic.sbs_frame(13, 0, W, H, D)
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=1)) as ctx:
+        res = ctx.depth_frames(torch.from_numpy(frame)[None].cuda(), False, want=("disp", "u16"))
+        disp, u16 = res["disp"][0].cpu().numpy(), _u16(res["u16"][0])
+        assert ctx.fused_sweep_clusters > 0
+    m = cv2_chain.make_matcher(D, 1)
+    l, r = cv2_chain.split_sbs_frame(frame, False)
+    ref = m.compute(cv2_chain.to_gray(l), cv2_chain.to_gray(r))
+    assert np.array_equal(disp, ref)
+    assert np.array_equal(u16, cv2_chain.normalize_u16(cv2_chain.depth_from_sbs(frame, m, False)))
+    assert (disp != -16).mean() > 0.4
+
+
+def test_bench_call_full_size_host_and_device_vs_oracle():
+    """The exact calls bench.py times, at its shapes: depth_frames(sbs, guide) (device-resident) and
+    depth_frames_host(sbs, guide) (pinned host buffers) on full-SBS 3840x1080 + a 3840x2160 guide.  The 4K uint16
+    output must be within 1 LSB of oracle.guided fed with the cv2 chain's uint16 depth, and both entry points
+    must agree bit for bit."""
+    W, H, D, B = 1920, 1080, 128, 2
+    frames = np.stack([synthetic.sbs_frame(11, t, W, H, D) for t in range(B)])
+    guides = np.stack([synthetic.guide_frame(11, t, 2 * W, 2 * H) for t in range(B)])
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D), max_batch=B) as ctx:
+        dev = ctx.depth_frames(torch.from_numpy(frames).cuda(), False, torch.from_numpy(guides).cuda(), 8, 1e-3,
+                               want=("u16",))
+        dev4k, devu16 = _u16(dev["out4k"]), _u16(dev["u16"])
+        out_h = torch.empty((B, 2 * H, 2 * W), dtype=torch.uint16).pin_memory()
+        ctx.depth_frames_host(torch.from_numpy(frames).pin_memory(), False, torch.from_numpy(guides).pin_memory(), 8, 1e-3,
+                              out={"out4k": out_h})
+        host4k = out_h.numpy().view(np.uint16)
+    assert np.array_equal(dev4k, host4k)
+    m = cv2_chain.make_matcher(D, 0)
+    for b in range(B):
+        ref_u16 = cv2_chain.normalize_u16(cv2_chain.depth_from_sbs(frames[b], m, False))
+        assert np.array_equal(devu16[b], ref_u16)
+        if b == 0:      # the float64 oracle takes ~20 s per 4K frame
+            _, o4 = og.guided_upscale(ref_u16, guides[b], 8, 1e-3)
+            assert np.abs(host4k[b].astype(np.int64) - o4.astype(np.int64)).max() <= 1
+
+
+def test_async_host_calls_from_one_submit_thread():
+    """bench.py's end-to-end lane model: ONE host thread submits v3d_depth_frames_host_async on several contexts
+    (each on its own stream) and sleeps in v3d_host_wait; results equal the synchronous device path.  The
+    copy-only twin moves the same bytes and leaves the kernels out (launch count unchanged)."""
+    W, H, D, B, L = 320, 96, 64, 3, 3
+    frames = [np.stack([synthetic.sbs_frame(50 + k, t, W, H, D) for t in range(B)]) for k in range(L)]
+    guides = [np.stack([synthetic.guide_frame(50 + k, t, 2 * W, 2 * H) for t in range(B)]) for k in range(L)]
+    ctxs = [nv.Context(W, H, nv.SgbmParams(numDisparities=D), max_batch=B) for _ in range(L)]
+    streams = [torch.cuda.Stream() for _ in range(L)]
+    fh = [torch.from_numpy(f).pin_memory() for f in frames]
+    gh = [torch.from_numpy(g).pin_memory() for g in guides]
+    outs = [dict(disp=torch.empty((B, H, W), dtype=torch.int16).pin_memory(),
+                 out4k=torch.zeros((B, 2 * H, 2 * W), dtype=torch.uint16).pin_memory()) for _ in range(L)]
+    try:
+        for _ in range(3):                   # resubmission after a wait, several steps deep
+            for k in range(L):
+                ctxs[k].host_wait()
+                with torch.cuda.stream(streams[k]):
+                    ctxs[k].depth_frames_host(fh[k], False, gh[k], 8, 1e-3, out=outs[k], wait=False)
+        for k in range(L):
+            ctxs[k].host_wait()
+            ctxs[k].host_wait()              # idempotent
+        for k in range(L):
+            ref = ctxs[k].depth_frames(torch.from_numpy(frames[k]).cuda(), False, torch.from_numpy(guides[k]).cuda(), 8, 1e-3,
+                                       want=("disp",))
+            torch.cuda.synchronize()
+            assert torch.equal(ref["disp"].cpu(), outs[k]["disp"])
+            assert torch.equal(ref["out4k"].cpu().view(torch.int16), outs[k]["out4k"].view(torch.int16))
+        n0 = ctxs[0].launch_count
+        with torch.cuda.stream(streams[0]):
+            ctxs[0].host_copy_only(fh[0], gh[0], out={"out4k": outs[0]["out4k"]})
+        ctxs[0].host_wait()
+        assert ctxs[0].launch_count == n0
+        # upscale-only host entry (cfg3): uint16 depth maps of the context's eye size + guide -> 4K
+        d = np.stack([synthetic.depth_u16(5, t, W, H) for t in range(B)])
+        dh = torch.from_numpy(d.view(np.int16)).view(torch.uint16).pin_memory()
+        o = torch.empty((B, 2 * H, 2 * W), dtype=torch.uint16).pin_memory()
+        ctxs[1].guided_upscale_host(dh, gh[1], o, 8, 1e-3)
+        want = ctxs[1].guided_upscale(dh.cuda(), gh[1].cuda(), 8, 1e-3)
+        assert torch.equal(want.cpu().view(torch.int16), o.view(torch.int16))
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_row_checkpoints_cover_every_width_remainder():
+    """The left-to-right direction is re-run from a checkpoint per 8-pixel chunk, chunks counted from the right
+    end of the row: every W1 % 8 (and rows shorter than one chunk) must give cv2's disparities, S taps included."""
+    for W1 in (3, 8, 9, 15, 16, 17, 23, 31, 40, 41):
+        _run_stages(W1 + 64, 12, 64, 0)
+    _run_stages(128 + 21, 9, 128, 1)
+    _run_stages(256 + 13, 6, 256, 0)

@@ -478,7 +478,11 @@ int launch_guided_stream(v3d_ctx* ctx, const uint16_t* depth, int w, int h, cons
     dim3 grid(strips, segs, batch);
     const int TWC = (SNC - 2 * r) & ~7;
     dim3 grid_c((gw + TWC - 1) / TWC, segs, batch);
-    k_guided_coeff_s<RT, SNC, SR, SGC><<<grid_c, SNC, sm_c, st>>>(depth, w, h, guide, gw, gh, r, eps, seg, ctx->ab);
+    {
+        V3dScope scope(ctx, ST_GUIDED, st);
+        k_guided_coeff_s<RT, SNC, SR, SGC><<<grid_c, SNC, sm_c, st>>>(depth, w, h, guide, gw, gh, r, eps, seg, ctx->ab);
+    }
+    V3dScope scope(ctx, ST_GUIDED_APPLY, st);
     if (vec) k_guided_apply_s<RT, SNT, SRA, SGR, true><<<grid, SNT, sm_a, st>>>(ctx->ab, guide, gw, gh, r, seg, out, q);
     else k_guided_apply_s<RT, SNT, SRA, SGR, false><<<grid, SNT, sm_a, st>>>(ctx->ab, guide, gw, gh, r, seg, out, q);
     V3D_LAUNCHED(ctx, 2);
@@ -498,7 +502,6 @@ int v3d_launch_guided(v3d_ctx* ctx, const uint16_t* depth, int w, int h, const u
         V3D_CUDA(cudaMalloc(&ctx->ab, need));
         ctx->ab_bytes = need; ctx->bytes += need;
     }
-    V3dScope scope(ctx, ST_GUIDED, st);
     switch (r) {
         case 8: return launch_guided_stream<8>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);
         case 4: return launch_guided_stream<4>(ctx, depth, w, h, guide, gw, gh, batch, r, eps, out, q, st);

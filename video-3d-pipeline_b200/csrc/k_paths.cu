@@ -6,9 +6,9 @@
 // One WARP owns one path (a row for the horizontal directions, a wrapped column/diagonal for the
 // vertical ones) and walks it sequentially.  Lane l holds the 2*NR consecutive disparities
 // d = 2*NR*l .. 2*NR*l + 2*NR-1 as NR packed int16x2 registers, so one warp-step is one coalesced
-// 128*NR-byte load of C, the DPX packed min/add recurrence and one CREDUX warp-min.  S is written by the first
-// kernel of the chain (left-to-right rows), accumulated by the vertical sweeps (L2 reductions) and consumed by
-// the last one (right-to-left rows + winner-takes-all); sums of integers, so the order does not matter.
+// 128*NR-byte load of C, the DPX packed min/add recurrence and one CREDUX warp-min.  S is written by the
+// top-down vertical sweep, accumulated by the bottom-up one (MODE_HH, L2 reductions) and consumed by the last
+// kernel (both row directions + winner-takes-all, k_paths_h.cu); sums of integers, so the order does not matter.
 //   state kept per path:  M[d] = min(L[d] - min_d L, P2)      (the P2 clamp folds the "minL + P2" term)
 //   step:                 L[d] = C[d] + min(M[d], min(M[d-1], M[d+1]) + P1)
 // A predecessor outside the window contributes L = 0, i.e. M = 0, which is also the initial state.
@@ -360,18 +360,28 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
     const int wpb = 8;
     dim3 block(wpb * 32);
     dim3 gv((W1 + wpb - 1) / wpb, batch);
-    // Order of the chain (integer sums, so any order gives the same S): the left-to-right row kernel first, in
-    // WRITE mode -- it is HBM-bound and now moves two volumes instead of three -- then the vertical sweeps
-    // accumulate onto S (they are ALU-bound and have the bandwidth), then right-to-left fused with WTA.
-    int rc = v3d_launch_path_lr(ctx, batch, st);
-    if (rc) return rc;
+    // Order of the chain (integer sums, so any order gives the same S): the top-down vertical sweep WRITES S (C in,
+    // S out: two volume passes, no read-modify-write), a bottom-up sweep (MODE_HH) accumulates onto it, the
+    // left-to-right checkpoint pass reads C once more, and the last kernel reads C and S, re-runs left-to-right
+    // from the checkpoints, runs right-to-left and feeds the winner-takes-all: 6.25 volume passes per frame
+    // with the cost kernel's write, where "every direction reads C and read-modify-writes S" would need 16.
+    // The checkpoint pass depends on C only, so it runs on a side stream next to the vertical sweep (which is
+    // ALU-bound and leaves the SMs its clusters cannot occupy, and most of the HBM bandwidth, unused).
+    const bool side = ctx->side_stream != nullptr && !ctx->timing;
+    if (side) {
+        V3D_CUDA(cudaEventRecord(ctx->ev_fork, st));
+        V3D_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        int rc = v3d_launch_path_lr(ctx, batch, ctx->side_stream);
+        if (rc) return rc;
+        V3D_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+    }
     {
         V3dScope scope(ctx, ST_PATHS, st);
         // top-down sweep: predecessors (x, y-1), (x-1, y-1), (x+1, y-1)
-        int fused = try_vert3<NR>(ctx, batch, +1, true, st);
+        int fused = try_vert3<NR>(ctx, batch, +1, false, st);
         if (fused < 0) return fused;
         if (!fused) {
-            k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, +1, P1p, P2p);
+            k_path_vert<NR, S_WRITE, PF><<<gv, block, 0, st>>>(C, S, W1, H, 0, +1, P1p, P2p);
             k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, +1, +1, P1p, P2p);
             k_path_vert<NR, S_ACCUM, PF><<<gv, block, 0, st>>>(C, S, W1, H, -1, +1, P1p, P2p);
             V3D_LAUNCHED(ctx, 3);
@@ -388,6 +398,8 @@ int launch_paths_nr(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
             }
         }
     }
+    if (side) V3D_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    else if (int rc = v3d_launch_path_lr(ctx, batch, st)) return rc;
     return v3d_launch_path_rl_wta(ctx, batch, st);
 }
 

@@ -2,9 +2,10 @@
 // One warp walks one image row.  A row of C (and of S) is a single contiguous run of
 // W1 * D * 2 bytes, so instead of one 128*NR-byte load per pixel step the warp's elected lane streams
 // it through shared memory in CH-pixel chunks with cp.async.bulk (SASS: UBLKCP) completing on an
-// mbarrier, NST chunks deep.  The left-to-right pass (first kernel of the chain) writes L into its
-// shared-memory stage and sends the chunk to S with a bulk store; the right-to-left pass (last kernel)
-// only reads: S_total feeds the winner-takes-all directly and never returns to memory.
+// mbarrier, NST chunks deep.  Neither horizontal direction writes a volume: the left-to-right pass only
+// leaves a checkpoint of its path state per chunk, the right-to-left pass (last kernel of the chain) re-runs
+// the left-to-right steps of each chunk from its checkpoint, adds both directions onto the vertical
+// directions' S in shared memory and feeds the winner-takes-all directly -- S_total never returns to memory.
 // Replaces the per-row part of OpenCV computeDisparitySGBM (depth.py:341).  Spec: SURVEY.md A.3/A.4.
 #include "path_common.cuh"
 #include "tma.cuh"
@@ -15,27 +16,37 @@ constexpr int HW_WARPS = 8;   // warps (rows) per block
 constexpr int CH = 8;         // pixel steps per staged chunk
 
 // ------------------------------------------------------------------------------------------
-// left -> right (predecessor x-1):  S = L.  This is the FIRST path kernel of the chain: it only streams C in
-// and S out (two volume passes), so the HBM-bound row kernel carries no read-modify-write; the vertical sweep,
-// which is ALU-bound and has HBM bandwidth to spare, accumulates onto S instead.
+// left -> right (predecessor x-1), CHECKPOINT pass.  The left-to-right costs L are never written: this kernel
+// only streams C in (one volume pass) and keeps, for every CH-pixel chunk of the right-to-left kernel below, the
+// path state M that ENTERS the chunk (1/CH of a volume).  The right-to-left kernel re-runs the CH left-to-right
+// steps of a chunk from its checkpoint, on the C chunk it has staged anyway, so the left-to-right direction
+// costs 1 + 2/CH volume passes instead of the 3 of "write S, read S back" -- the recomputed steps land on a
+// kernel that is HBM-bound and has the issue slots.
+//   ckpt[row][c][d], c = chunk index counted from the RIGHT end of the row (chunk c = pixels [W1-8c-8, W1-8c)),
+//   = M before the chunk's first pixel; the left-most chunk starts a path (M = 0) and has no checkpoint.
 // ------------------------------------------------------------------------------------------
+#ifndef V3D_LRC_NST
+#define V3D_LRC_NST 4
+#endif
+__host__ __device__ constexpr int lrc_stages(int nr) { return nr == 4 ? 3 : V3D_LRC_NST; }   // D = 256: two blocks per SM
 template <int NR>
 __global__ void __launch_bounds__(HW_WARPS * 32)
-k_path_lr_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, int rows, uint32_t P1p, uint32_t P2p)
+k_path_lr_ckpt(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ ckpt, int W1, int rows, uint32_t P1p, uint32_t P2p)
 {
     using VT = typename Vec<NR>::T;
-    constexpr int NST = 3;
+    constexpr int NST = lrc_stages(NR);
     constexpr int STEP_B = 128 * NR;                 // bytes of one pixel's D costs
     extern __shared__ __align__(128) unsigned char hsm[];
     __shared__ __align__(8) uint64_t bars[HW_WARPS][NST];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int row = blockIdx.x * HW_WARPS + wib;
     if (row >= rows) return;
-    unsigned char* cst = hsm + (size_t)wib * (2 * NST * CH * STEP_B);   // [NST][CH][STEP_B]
-    unsigned char* sst = cst + NST * CH * STEP_B;
+    unsigned char* cst = hsm + (size_t)wib * (NST * CH * STEP_B);   // [NST][CH][STEP_B]
     const unsigned char* Cg = reinterpret_cast<const unsigned char*>(Cv) + (size_t)row * W1 * STEP_B;
-    unsigned char* Sg = reinterpret_cast<unsigned char*>(Sv) + (size_t)row * W1 * STEP_B;
     const int nchunks = (W1 + CH - 1) / CH;
+    VT* ck = reinterpret_cast<VT*>(ckpt) + (size_t)row * nchunks * 32 + lane;
+    const int jstar = W1 & (CH - 1);                 // position inside a left-aligned chunk where a right-aligned chunk starts
+    const int c_of_k0 = (W1 / CH) - 1;               // right-aligned chunk that starts inside left-aligned chunk 0
 
     if (lane == 0) {
 #pragma unroll
@@ -51,8 +62,9 @@ k_path_lr_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1
         bulk_g2s(cst + st * CH * STEP_B, Cg + (size_t)x0 * STEP_B, bytes, &bars[wib][st]);
     };
     if (lane == 0) {
-        issue(0);
-        if (nchunks > 1) issue(1);
+#pragma unroll
+        for (int s = 0; s < NST - 1; s++)
+            if (s < nchunks) issue(s);
     }
     uint32_t M[NR];
 #pragma unroll
@@ -60,57 +72,52 @@ k_path_lr_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1
     for (int c = 0; c < nchunks; c++) {
         const int st = c % NST;
         mbar_wait(&bars[wib][st], (uint32_t)((c / NST) & 1));
+        // every lane has left chunk c-1 (the __syncwarp below): its stage takes chunk c+NST-1
+        if (lane == 0 && c + NST - 1 < nchunks) issue(c + NST - 1);
         const VT* cs = reinterpret_cast<const VT*>(cst + st * CH * STEP_B) + lane;
-        VT* ss = reinterpret_cast<VT*>(sst + st * CH * STEP_B) + lane;
         const int n = min(CH, W1 - c * CH);
+        const int cr = c_of_k0 - c;                  // checkpoint taken inside this chunk (if any)
+        const bool take = cr >= 0 && (c > 0 || jstar > 0);
         if (n == CH) {
 #pragma unroll
             for (int j = 0; j < CH; j++) {
+                if (take && j == jstar) ck[(size_t)cr * 32] = pack<NR>(M);
                 uint32_t Cr[NR], L[NR];
                 unpack<NR>(cs[j * 32], Cr);
                 path_step<NR>(M, Cr, L, P1p, P2p, lane);
-                ss[j * 32] = pack<NR>(L);
             }
         } else {
             for (int j = 0; j < n; j++) {
+                if (take && j == jstar) ck[(size_t)cr * 32] = pack<NR>(M);
                 uint32_t Cr[NR], L[NR];
                 unpack<NR>(cs[j * 32], Cr);
                 path_step<NR>(M, Cr, L, P1p, P2p, lane);
-                ss[j * 32] = pack<NR>(L);
             }
         }
-        fence_async_smem();          // generic-proxy writes of every lane -> visible to the bulk store
-        __syncwarp();
-        if (lane == 0) {
-            bulk_s2g(Sg + (size_t)c * CH * STEP_B, sst + st * CH * STEP_B, (uint32_t)n * STEP_B);
-            bulk_commit();
-            if (c + 2 < nchunks) {
-                bulk_wait_read<1>();   // the store issued one chunk ago has finished reading stage (c+2)%NST
-                issue(c + 2);
-            }
-        }
-        __syncwarp();
+        __syncwarp();                                // every lane is done reading this stage
     }
-    if (lane == 0) bulk_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------
-// right -> left (predecessor x+1) fused with winner-takes-all.  Per pixel one 8-byte record:
+// right -> left (predecessor x+1) fused with the re-run of the left -> right steps and winner-takes-all.
+// Per pixel one 8-byte record:
 //   .x = minS | best << 16      (best = 0xffff when the uniqueness test rejects the pixel)
 //   .y = S[best-1] | S[best+1] << 16
 // which k_select turns into the disparity (disp2 vote, sub-pixel, LR check).
 //
-// Per chunk of CH = 8 pixels the warp first walks the 8 path steps (lane = 2*NR consecutive
-// disparities, S_total written in place into the staged S chunk), then re-maps its lanes to
-// (pixel = lane / 4, quarter = lane % 4) so that all 8 pixels do their winner-takes-all at once:
-// each lane scans its quarter of one pixel's disparities from shared memory and the four quarters
+// Per chunk of CH = 8 pixels the warp stages C, S (the vertical directions' sum) and the left-to-right
+// checkpoint of the chunk, then walks the chunk in BOTH directions at once: step i runs the left-to-right
+// recurrence at pixel i and the right-to-left one at pixel 7-i -- two independent dependency chains in one
+// instruction stream -- and adds both L onto S in place.  After that the chunk holds S_total and the warp
+// re-maps its lanes to (pixel = lane / 4, quarter = lane % 4) so that all 8 pixels do their winner-takes-all at
+// once: each lane scans its quarter of one pixel's disparities from shared memory and the four quarters
 // meet through two shuffle-xor steps.  That replaces two warp-wide reductions per PIXEL by two
-// 4-lane reductions per CHUNK.
+// 4-lane reductions per CHUNK.  S_total never returns to memory.
 // ------------------------------------------------------------------------------------------
 template <int NR, bool TAP_S, bool PAD>
 __global__ void __launch_bounds__(HW_WARPS * 32)
-k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, uint2* __restrict__ rec, int W1,
-                  int rows, uint32_t P1p, uint32_t P2p, int uniq, int Dreal)
+k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, const uint16_t* __restrict__ ckpt,
+                  uint2* __restrict__ rec, int W1, int rows, uint32_t P1p, uint32_t P2p, int uniq, int Dreal)
 {
     using VT = typename Vec<NR>::T;
     constexpr int D = 64 * NR;
@@ -123,13 +130,15 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, ui
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int row = blockIdx.x * HW_WARPS + wib;
     if (row >= rows) return;
-    unsigned char* cst = hsm + (size_t)wib * (2 * NST * CH * STEP_B);
+    unsigned char* cst = hsm + (size_t)wib * ((2 * CH + 1) * NST * STEP_B);   // [NST][CH][STEP_B] C, the same for S, [NST][STEP_B] checkpoints
     unsigned char* sst = cst + NST * CH * STEP_B;
+    unsigned char* kst = sst + NST * CH * STEP_B;
     const unsigned char* Cg = reinterpret_cast<const unsigned char*>(Cv) + (size_t)row * W1 * STEP_B;
     const unsigned char* Sg = reinterpret_cast<const unsigned char*>(Sv) + (size_t)row * W1 * STEP_B;
     uint4* Stap = reinterpret_cast<uint4*>(Sv) + (size_t)row * W1 * (STEP_B / 16);
     rec += (size_t)row * W1;
     const int nchunks = (W1 + CH - 1) / CH;
+    const unsigned char* Kg = reinterpret_cast<const unsigned char*>(ckpt) + (size_t)row * nchunks * STEP_B;
 
     // WTA-phase identity of this lane
     const int wp = lane >> 2, wq = lane & 3;
@@ -148,9 +157,10 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, ui
         const int st = c % NST;
         const int hi = W1 - c * CH, lo = max(hi - CH, 0);
         const uint32_t bytes = (uint32_t)(hi - lo) * STEP_B;
-        mbar_expect_tx(&bars[wib][st], 2 * bytes);
+        mbar_expect_tx(&bars[wib][st], 2 * bytes + (lo > 0 ? STEP_B : 0));
         bulk_g2s(cst + st * CH * STEP_B, Cg + (size_t)lo * STEP_B, bytes, &bars[wib][st]);
         bulk_g2s(sst + st * CH * STEP_B, Sg + (size_t)lo * STEP_B, bytes, &bars[wib][st]);
+        if (lo > 0) bulk_g2s(kst + st * STEP_B, Kg + (size_t)c * STEP_B, STEP_B, &bars[wib][st]);   // the left-most chunk starts a path
     };
     if (lane == 0) {
         issue(0);
@@ -166,19 +176,41 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, ui
         const int hi = W1 - c * CH, lo = max(hi - CH, 0), n = hi - lo;
         const VT* cs = reinterpret_cast<const VT*>(cst + st * CH * STEP_B) + lane;
         VT* ss = reinterpret_cast<VT*>(sst + st * CH * STEP_B) + lane;
-        // ---- phase 1: the path steps, right to left; S_total replaces S in the stage ----
+        // ---- phase 1: the path steps of both horizontal directions; S_total replaces S in the stage ----
+        uint32_t Ml[NR];                             // left-to-right state entering the chunk
+        if (lo > 0) unpack<NR>(reinterpret_cast<const VT*>(kst + st * STEP_B)[lane], Ml);
+        else {
+#pragma unroll
+            for (int r = 0; r < NR; r++) Ml[r] = 0;
+        }
         if (n == CH) {
 #pragma unroll
-            for (int j = CH - 1; j >= 0; j--) {
+            for (int i = 0; i < CH; i++) {
+                const int j = CH - 1 - i;
+                uint32_t Ca[NR], Cb[NR], Sa[NR], Sb[NR], La[NR], Lb[NR];
+                unpack<NR>(cs[i * 32], Ca);
+                unpack<NR>(cs[j * 32], Cb);
+                path_step<NR>(Ml, Ca, La, P1p, P2p, lane);       // left to right at pixel i
+                path_step<NR>(M, Cb, Lb, P1p, P2p, lane);        // right to left at pixel 7 - i
+                unpack<NR>(ss[i * 32], Sa);
+#pragma unroll
+                for (int r = 0; r < NR; r++) Sa[r] += La[r];
+                ss[i * 32] = pack<NR>(Sa);
+                unpack<NR>(ss[j * 32], Sb);                      // (i and j never coincide: CH is even)
+#pragma unroll
+                for (int r = 0; r < NR; r++) Sb[r] += Lb[r];
+                ss[j * 32] = pack<NR>(Sb);
+            }
+        } else {
+            for (int j = 0; j < n; j++) {
                 uint32_t Cr[NR], Sr[NR], L[NR];
                 unpack<NR>(cs[j * 32], Cr);
                 unpack<NR>(ss[j * 32], Sr);
-                path_step<NR>(M, Cr, L, P1p, P2p, lane);
+                path_step<NR>(Ml, Cr, L, P1p, P2p, lane);
 #pragma unroll
                 for (int r = 0; r < NR; r++) Sr[r] += L[r];
                 ss[j * 32] = pack<NR>(Sr);
             }
-        } else {
             for (int j = n - 1; j >= 0; j--) {
                 uint32_t Cr[NR], Sr[NR], L[NR];
                 unpack<NR>(cs[j * 32], Cr);
@@ -251,11 +283,11 @@ int launch_lr(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     const int rows = batch * ctx->H;
     const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
-    const size_t smem = (size_t)HW_WARPS * 2 * 3 * CH * 128 * NR;
+    const size_t smem = (size_t)HW_WARPS * lrc_stages(NR) * CH * 128 * NR;
     dim3 grid((rows + HW_WARPS - 1) / HW_WARPS), block(HW_WARPS * 32);
-    V3D_CUDA(cudaFuncSetAttribute(k_path_lr_tma<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    V3D_CUDA(cudaFuncSetAttribute(k_path_lr_ckpt<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     V3dScope scope(ctx, ST_LR, st);
-    k_path_lr_tma<NR><<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->W1, rows, P1p, P2p);
+    k_path_lr_ckpt<NR><<<grid, block, smem, st>>>(ctx->C, ctx->ckpt, ctx->W1, rows, P1p, P2p);
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
@@ -265,21 +297,21 @@ int launch_wta(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
 {
     const int rows = batch * ctx->H;
     const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
-    const size_t smem = (size_t)HW_WARPS * 2 * 3 * CH * 128 * NR;
+    const size_t smem = (size_t)HW_WARPS * (2 * CH + 1) * 3 * 128 * NR;
     dim3 grid((rows + HW_WARPS - 1) / HW_WARPS), block(HW_WARPS * 32);
     const bool pad = ctx->D != ctx->Dk;
     auto wta = tap_s ? (pad ? k_path_rl_wta_tma<NR, true, true> : k_path_rl_wta_tma<NR, true, false>)
                      : (pad ? k_path_rl_wta_tma<NR, false, true> : k_path_rl_wta_tma<NR, false, false>);
     V3D_CUDA(cudaFuncSetAttribute(wta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     V3dScope scope(ctx, ST_WTA, st);
-    wta<<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->rec, ctx->W1, rows, P1p, P2p, ctx->uniq, ctx->D);
+    wta<<<grid, block, smem, st>>>(ctx->C, ctx->S, ctx->ckpt, ctx->rec, ctx->W1, rows, P1p, P2p, ctx->uniq, ctx->D);
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
 
 }  // namespace
 
-// first path kernel: S = L(left -> right)
+// left-to-right checkpoint pass: reads C, writes the path state entering every 8-pixel chunk
 int v3d_launch_path_lr(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     switch (ctx->Dk) {
@@ -290,7 +322,7 @@ int v3d_launch_path_lr(v3d_ctx* ctx, int batch, cudaStream_t st)
     return v3d_fail(V3D_EINVAL, "numDisparities %d unsupported (64, 128, 256)", ctx->D);
 }
 
-// last path kernel: right -> left fused with winner-takes-all
+// last path kernel: both horizontal directions (left-to-right re-run from the checkpoints) fused with winner-takes-all
 int v3d_launch_path_rl_wta(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     const bool tap_s = ctx->debug_taps != 0;   // parity tests ask the WTA pass to also store S_total

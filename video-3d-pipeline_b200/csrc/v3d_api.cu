@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -10,7 +11,7 @@
 namespace {
 thread_local char g_err[512] = "";
 const char* const kStageNames[ST_COUNT] = { "split_gray", "prefilter", "cost", "vertical", "lr", "wta", "select",
-                                            "median", "speckle", "post", "guided", "copy" };
+                                            "median", "speckle", "post", "guided_coeff", "guided_apply", "copy" };
 }  // namespace
 
 int v3d_fail(int code, const char* fmt, ...)
@@ -80,7 +81,7 @@ void v3d_default_params(v3d_sgbm_params* p)
 
 static void free_all(v3d_ctx* c)
 {
-    void* ptrs[] = { c->grayL, c->grayR, c->rexp, c->lexp, c->C, c->S, c->rec, c->raw, c->med, c->disp, c->labels,
+    void* ptrs[] = { c->grayL, c->grayR, c->rexp, c->lexp, c->C, c->S, c->ckpt, c->rec, c->raw, c->med, c->disp, c->labels,
                      c->sizes, c->minmax, c->png_sums, c->f32_tmp, c->u16_tmp, c->ab, c->in_dev, c->guide_dev, c->out_dev };
     for (void* p : ptrs) if (p) cudaFree(p);
 }
@@ -144,6 +145,7 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
         { (void**)&c->rexp, B * eye_h * 4 * (size_t)c->rexp_wpw * sizeof(uint4) },
         { (void**)&c->lexp, B * eye_h * (size_t)v3d_lexp_cols(eye_w) * 2 * sizeof(uint4) },
         { (void**)&c->C, vol }, { (void**)&c->S, vol },
+        { (void**)&c->ckpt, B * (size_t)eye_h * ((c->W1 + 7) / 8) * c->Dk * sizeof(uint16_t) },
         { (void**)&c->rec, B * (size_t)eye_h * c->W1 * sizeof(uint2) },
         { (void**)&c->raw, B * npx * 2 }, { (void**)&c->med, B * npx * 2 }, { (void**)&c->disp, B * npx * 2 },
         { (void**)&c->labels, B * npx * 4 }, { (void**)&c->sizes, B * npx * 4 },
@@ -160,6 +162,16 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
         }
         c->bytes += a.n;
     }
+    // side stream of the path chain (k_paths.cu); V3D_NO_SIDE_STREAM=1 keeps the chain on one stream
+    const char* ns = getenv("V3D_NO_SIDE_STREAM");
+    if (!(ns && ns[0] == '1')) {
+        if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            c->side_stream = nullptr;
+        }
+    }
     *out = c;
     return V3D_OK;
 }
@@ -170,7 +182,12 @@ int v3d_destroy(v3d_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     drain_spans(ctx);
-    if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_done); }
+    if (ctx->side_stream) { cudaStreamDestroy(ctx->side_stream); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
+    if (ctx->up_stream) {
+        cudaStreamDestroy(ctx->up_stream); cudaStreamDestroy(ctx->down_stream);
+        cudaEvent_t evs[] = { ctx->ev_entry, ctx->ev_sbs, ctx->ev_guide, ctx->ev_compute, ctx->ev_done };
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    }
     free_all(ctx);
     delete ctx;
     return V3D_OK;
@@ -398,53 +415,176 @@ static int ensure(v3d_ctx* ctx, void** p, size_t* have, size_t need)
     return V3D_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// One asynchronous host call: which host buffers go in and come out.
+struct HostJob {
+    const uint8_t* sbs = nullptr; int sbs_w = 0, h = 0, unsqueeze = 0;      // SBS frames in (NULL: upscale only)
+    const uint16_t* depth_in = nullptr;                                     // uint16 depth in (upscale only)
+    const uint8_t* guide = nullptr; int gw = 0, gh = 0, r = 0; float eps = 0.f;
+    int16_t* disp = nullptr; float* f32 = nullptr; uint16_t* u16 = nullptr; uint16_t* out4k = nullptr;
+    int batch = 0;
+    bool copy_only = false;                                                 // same copies, no kernels
+};
+
+int host_streams(v3d_ctx* ctx)
+{
+    if (ctx->up_stream) return V3D_OK;
+    V3D_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+    V3D_CUDA(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+    cudaEvent_t* evs[] = { &ctx->ev_entry, &ctx->ev_sbs, &ctx->ev_guide, &ctx->ev_compute };
+    for (cudaEvent_t* e : evs) V3D_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    // the host waits on this one: blocking sync = the thread sleeps on an OS primitive instead of spinning, so
+    // many lanes and ranks can share few host cores
+    V3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
+    return V3D_OK;
+}
+
+// Enqueue one host call.  Three streams: uploads (frame by frame, SBS first: the SGBM chain starts as soon as the
+// SBS frames are in and runs under the guide upload), kernels on the caller's stream, downloads (frame by frame).
+// The caller's stream finally waits for the downloads, so the call stays stream-ordered as a whole.
+int host_submit(v3d_ctx* ctx, const HostJob& j, cudaStream_t st)
+{
+    int rc;
+    const int B = j.batch;
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    const size_t sbs_frame = (size_t)j.sbs_w * j.h * 3;
+    const size_t guide_frame = (size_t)j.gw * j.gh * 3, out_frame = (size_t)j.gw * j.gh * 2;
+    if ((rc = host_streams(ctx))) return rc;
+    if (j.sbs && (rc = ensure(ctx, (void**)&ctx->in_dev, &ctx->in_bytes, sbs_frame * B))) return rc;
+    if (j.guide) {
+        if ((rc = ensure(ctx, (void**)&ctx->guide_dev, &ctx->guide_bytes, guide_frame * B))) return rc;
+        if ((rc = ensure(ctx, (void**)&ctx->out_dev, &ctx->out_bytes, out_frame * B))) return rc;
+    }
+    cudaStream_t up = ctx->up_stream, down = ctx->down_stream;
+    V3D_CUDA(cudaEventRecord(ctx->ev_entry, st));
+    V3D_CUDA(cudaStreamWaitEvent(up, ctx->ev_entry, 0));
+    {
+        V3dScope scope(ctx, ST_COPY, up);
+        if (j.sbs)
+            for (int f = 0; f < B; f++)
+                V3D_CUDA(cudaMemcpyAsync(ctx->in_dev + f * sbs_frame, j.sbs + f * sbs_frame, sbs_frame, cudaMemcpyHostToDevice, up));
+        if (j.depth_in)
+            V3D_CUDA(cudaMemcpyAsync(ctx->u16_tmp, j.depth_in, npx * 2 * B, cudaMemcpyHostToDevice, up));
+        V3D_CUDA(cudaEventRecord(ctx->ev_sbs, up));
+        if (j.guide) {
+            for (int f = 0; f < B; f++)
+                V3D_CUDA(cudaMemcpyAsync(ctx->guide_dev + f * guide_frame, j.guide + f * guide_frame, guide_frame, cudaMemcpyHostToDevice, up));
+            V3D_CUDA(cudaEventRecord(ctx->ev_guide, up));
+        }
+    }
+    V3D_CUDA(cudaStreamWaitEvent(st, ctx->ev_sbs, 0));
+    if (j.sbs && !j.copy_only) {
+        rc = v3d_depth_frames(ctx, ctx->in_dev, (size_t)j.sbs_w * 3, sbs_frame, j.sbs_w, j.h, B, j.unsqueeze, ctx->disp,
+                              j.f32 ? ctx->f32_tmp : nullptr, j.u16 || j.guide ? ctx->u16_tmp : nullptr,
+                              nullptr, 0, 0, j.r, j.eps, nullptr, st);
+        if (rc) return rc;
+    }
+    if (j.guide) {
+        V3D_CUDA(cudaStreamWaitEvent(st, ctx->ev_guide, 0));
+        if (!j.copy_only)
+            if ((rc = v3d_guided_upscale(ctx, ctx->u16_tmp, ctx->W, ctx->H, ctx->guide_dev, j.gw, j.gh, B, j.r, j.eps,
+                                         ctx->out_dev, nullptr, st))) return rc;
+    }
+    V3D_CUDA(cudaEventRecord(ctx->ev_compute, st));
+    V3D_CUDA(cudaStreamWaitEvent(down, ctx->ev_compute, 0));
+    {
+        V3dScope scope(ctx, ST_COPY, down);
+        if (j.disp) V3D_CUDA(cudaMemcpyAsync(j.disp, ctx->disp, npx * 2 * B, cudaMemcpyDeviceToHost, down));
+        if (j.f32) V3D_CUDA(cudaMemcpyAsync(j.f32, ctx->f32_tmp, npx * 4 * B, cudaMemcpyDeviceToHost, down));
+        if (j.u16) V3D_CUDA(cudaMemcpyAsync(j.u16, ctx->u16_tmp, npx * 2 * B, cudaMemcpyDeviceToHost, down));
+        if (j.out4k)
+            for (int f = 0; f < B; f++)
+                V3D_CUDA(cudaMemcpyAsync(j.out4k + f * (out_frame / 2), ctx->out_dev + f * (out_frame / 2), out_frame,
+                                         cudaMemcpyDeviceToHost, down));
+    }
+    V3D_CUDA(cudaEventRecord(ctx->ev_done, down));
+    V3D_CUDA(cudaStreamWaitEvent(st, ctx->ev_done, 0));
+    ctx->host_pending = 1;
+    ctx->host_calls++;
+    return V3D_OK;
+}
+
+int check_frames_host_args(v3d_ctx* ctx, const uint8_t* sbs, int sbs_w, int h, int batch, int unsqueeze,
+                           const uint8_t* guide, int gw, int gh, const uint16_t* out4k)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!sbs) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (sbs_w <= 0 || (sbs_w & 1)) return v3d_fail(V3D_EINVAL, "SBS frame width must be even");
+    const int eye_w = unsqueeze ? sbs_w : sbs_w / 2;
+    if (eye_w != ctx->W || h != ctx->H)
+        return v3d_fail(V3D_EINVAL, "frame gives %dx%d eyes, context was created for %dx%d", eye_w, h, ctx->W, ctx->H);
+    if (guide && !out4k) return v3d_fail(V3D_EINVAL, "guide given without an output buffer");
+    if (guide && (gw <= 0 || gh <= 0 || gw > 32768 || gh > 32768)) return v3d_fail(V3D_EINVAL, "bad guide size");
+    return V3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int v3d_depth_frames_host_async(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, int h, int batch, int unsqueeze,
+                                int16_t* disp_host, float* depth_f32_host, uint16_t* depth_u16_host,
+                                const uint8_t* guide_rgb_host, int gw, int gh, int r, float eps, uint16_t* out_4k_host,
+                                void* stream)
+{
+    if (int rc = check_frames_host_args(ctx, sbs_bgr_host, sbs_w, h, batch, unsqueeze, guide_rgb_host, gw, gh, out_4k_host))
+        return rc;
+    if (guide_rgb_host && !(eps > 0.f)) return v3d_fail(V3D_EINVAL, "eps must be positive");
+    HostJob j;
+    j.sbs = sbs_bgr_host; j.sbs_w = sbs_w; j.h = h; j.unsqueeze = unsqueeze; j.batch = batch;
+    j.disp = disp_host; j.f32 = depth_f32_host; j.u16 = depth_u16_host;
+    j.guide = guide_rgb_host; j.gw = gw; j.gh = gh; j.r = r; j.eps = eps; j.out4k = out_4k_host;
+    return host_submit(ctx, j, (cudaStream_t)stream);
+}
+
+int v3d_guided_upscale_host_async(v3d_ctx* ctx, const uint16_t* depth_u16_host, const uint8_t* guide_rgb_host, int gw,
+                                  int gh, int batch, int r, float eps, uint16_t* out_u16_host, void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!depth_u16_host || !guide_rgb_host || !out_u16_host) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (gw <= 0 || gh <= 0 || gw > 32768 || gh > 32768) return v3d_fail(V3D_EINVAL, "bad guide size");
+    if (!(eps > 0.f)) return v3d_fail(V3D_EINVAL, "eps must be positive");
+    HostJob j;
+    j.depth_in = depth_u16_host; j.batch = batch;
+    j.guide = guide_rgb_host; j.gw = gw; j.gh = gh; j.r = r; j.eps = eps; j.out4k = out_u16_host;
+    return host_submit(ctx, j, (cudaStream_t)stream);
+}
+
+int v3d_host_copy_only_async(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, int h, int batch, int16_t* disp_host,
+                             const uint8_t* guide_rgb_host, int gw, int gh, uint16_t* out_4k_host, void* stream)
+{
+    if (int rc = check_batch(ctx, batch)) return rc;
+    if (!sbs_bgr_host && !guide_rgb_host) return v3d_fail(V3D_EINVAL, "null buffer");
+    if (guide_rgb_host && !out_4k_host) return v3d_fail(V3D_EINVAL, "guide given without an output buffer");
+    HostJob j;
+    j.sbs = sbs_bgr_host; j.sbs_w = sbs_w; j.h = h; j.batch = batch; j.disp = disp_host;
+    j.guide = guide_rgb_host; j.gw = gw; j.gh = gh; j.out4k = out_4k_host;
+    j.copy_only = true;
+    return host_submit(ctx, j, (cudaStream_t)stream);
+}
+
+int v3d_host_wait(v3d_ctx* ctx)
+{
+    if (!ctx) return v3d_fail(V3D_EINVAL, "null context");
+    if (!ctx->host_pending) return V3D_OK;
+    V3D_CUDA(cudaSetDevice(ctx->device));
+    ctx->host_pending = 0;
+    V3D_CUDA(cudaEventSynchronize(ctx->ev_done));
+    return V3D_OK;
+}
+
 int v3d_depth_frames_host(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, int h, int batch, int unsqueeze,
                           int16_t* disp_host, float* depth_f32_host, uint16_t* depth_u16_host,
                           const uint8_t* guide_rgb_host, int gw, int gh, int r, float eps, uint16_t* out_4k_host,
                           void* stream)
 {
-    if (int rc = check_batch(ctx, batch)) return rc;
-    if (!sbs_bgr_host) return v3d_fail(V3D_EINVAL, "null buffer");
-    if (guide_rgb_host && !out_4k_host) return v3d_fail(V3D_EINVAL, "guide given without an output buffer");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t frame = (size_t)sbs_w * h * 3, npx = (size_t)ctx->W * ctx->H;
-    int rc;
-    if ((rc = ensure(ctx, (void**)&ctx->in_dev, &ctx->in_bytes, frame * batch))) return rc;
-    {
-        V3dScope scope(ctx, ST_COPY, st);
-        V3D_CUDA(cudaMemcpyAsync(ctx->in_dev, sbs_bgr_host, frame * batch, cudaMemcpyHostToDevice, st));
-        if (guide_rgb_host) {
-            // the guide (2/3 of the input bytes) is not needed before the upscale: upload it on the
-            // context's copy stream so that it overlaps the whole SGBM chain
-            const size_t gbytes = (size_t)gw * gh * 3 * batch;
-            if ((rc = ensure(ctx, (void**)&ctx->guide_dev, &ctx->guide_bytes, gbytes))) return rc;
-            if ((rc = ensure(ctx, (void**)&ctx->out_dev, &ctx->out_bytes, (size_t)gw * gh * 2 * batch))) return rc;
-            if (!ctx->copy_stream) {
-                V3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-                V3D_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
-            }
-            V3D_CUDA(cudaMemcpyAsync(ctx->guide_dev, guide_rgb_host, gbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-            V3D_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
-        }
-    }
-    rc = v3d_depth_frames(ctx, ctx->in_dev, (size_t)sbs_w * 3, frame, sbs_w, h, batch, unsqueeze, ctx->disp,
-                          depth_f32_host ? ctx->f32_tmp : nullptr, depth_u16_host || guide_rgb_host ? ctx->u16_tmp : nullptr,
-                          nullptr, 0, 0, r, eps, nullptr, stream);
-    if (rc) return rc;
-    if (guide_rgb_host) {
-        V3D_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
-        if ((rc = v3d_guided_upscale(ctx, ctx->u16_tmp, ctx->W, ctx->H, ctx->guide_dev, gw, gh, batch, r, eps,
-                                     ctx->out_dev, nullptr, stream))) return rc;
-    }
-    {
-        V3dScope scope(ctx, ST_COPY, st);
-        if (disp_host) V3D_CUDA(cudaMemcpyAsync(disp_host, ctx->disp, npx * 2 * batch, cudaMemcpyDeviceToHost, st));
-        if (depth_f32_host) V3D_CUDA(cudaMemcpyAsync(depth_f32_host, ctx->f32_tmp, npx * 4 * batch, cudaMemcpyDeviceToHost, st));
-        if (depth_u16_host) V3D_CUDA(cudaMemcpyAsync(depth_u16_host, ctx->u16_tmp, npx * 2 * batch, cudaMemcpyDeviceToHost, st));
-        if (out_4k_host) V3D_CUDA(cudaMemcpyAsync(out_4k_host, ctx->out_dev, (size_t)gw * gh * 2 * batch, cudaMemcpyDeviceToHost, st));
-    }
-    V3D_CUDA(cudaStreamSynchronize(st));
-    return V3D_OK;
+    if (int rc = v3d_depth_frames_host_async(ctx, sbs_bgr_host, sbs_w, h, batch, unsqueeze, disp_host, depth_f32_host,
+                                             depth_u16_host, guide_rgb_host, gw, gh, r, eps, out_4k_host, stream))
+        return rc;
+    return v3d_host_wait(ctx);
 }
 
 }  // extern "C"

@@ -10,7 +10,7 @@
 
 enum V3dStage {
     ST_SPLIT_GRAY = 0, ST_PREFILTER, ST_COST, ST_PATHS, ST_LR, ST_WTA, ST_SELECT, ST_MEDIAN,
-    ST_SPECKLE, ST_POST, ST_GUIDED, ST_COPY, ST_COUNT
+    ST_SPECKLE, ST_POST, ST_GUIDED, ST_GUIDED_APPLY, ST_COPY, ST_COUNT
 };
 
 struct V3dTimedSpan { int stage; cudaEvent_t a, b; };
@@ -28,6 +28,8 @@ struct v3d_ctx {
     uint4 *rexp, *lexp;          // expanded BT operands (k_cost.cu): right [B][H][2][2][rexp_wpw], left [B][H][W+16][2]
     int rexp_wpw;
     uint16_t *C, *S;             // [B][H][W1][D]
+    uint16_t* ckpt;              // [B][H][ceil(W1/8)][D] left-to-right path state entering every 8-pixel chunk (k_paths_h.cu)
+    cudaStream_t side_stream; cudaEvent_t ev_fork, ev_join;   // the checkpoint pass runs next to the vertical sweep
     uint2* rec;                  // WTA records [B][H][W1]
     int16_t *raw, *med, *disp;   // [B][H][W]
     int *labels, *sizes;         // [B][H*W]
@@ -40,7 +42,13 @@ struct v3d_ctx {
     uint8_t* in_dev; size_t in_bytes;      // host-API staging: SBS frames
     uint8_t* guide_dev; size_t guide_bytes;
     uint16_t* out_dev; size_t out_bytes;
-    cudaStream_t copy_stream; cudaEvent_t copy_done;   // host entry point: guide upload overlaps the SGBM chain
+    // host entry points (v3d_depth_frames_host_async): uploads and downloads run frame by frame on their own streams
+    // so that both DMA engines stay busy next to the kernels; completion is a blocking-sync event (the waiting host
+    // thread sleeps instead of spinning)
+    cudaStream_t up_stream, down_stream;
+    cudaEvent_t ev_entry, ev_sbs, ev_guide, ev_compute, ev_done;
+    int host_pending;        // an asynchronous host call has not been waited for yet
+    int host_calls;          // asynchronous host calls issued so far
     size_t bytes;
     int last_batch;
 

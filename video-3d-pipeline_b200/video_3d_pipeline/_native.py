@@ -17,7 +17,7 @@ V3D_EINVAL, V3D_ENOMEM, V3D_ECUDA, V3D_ESTATE = -1, -2, -3, -4
 INVALID_DISP = -16
 MODE_SGBM, MODE_HH = 0, 1
 
-STAGES = ("split_gray", "prefilter", "cost", "vertical", "lr", "wta", "select", "median", "speckle", "post", "guided", "copy")
+STAGES = ("split_gray", "prefilter", "cost", "vertical", "lr", "wta", "select", "median", "speckle", "post", "guided_coeff", "guided_apply", "copy")
 
 
 class SgbmParams(C.Structure):
@@ -64,6 +64,10 @@ def lib():
     L.v3d_guided_upscale.argtypes = [vp, vp, i32, i32, vp, i32, i32, i32, i32, C.c_float, vp, vp, vp]
     L.v3d_depth_frames.argtypes = [vp, vp, sz, sz, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, C.c_float, vp, vp]
     L.v3d_depth_frames_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, C.c_float, vp, vp]
+    L.v3d_depth_frames_host_async.argtypes = L.v3d_depth_frames_host.argtypes
+    L.v3d_guided_upscale_host_async.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.c_float, vp, vp]
+    L.v3d_host_copy_only_async.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]
+    L.v3d_host_wait.argtypes = [vp]
     L.v3d_fused_sweep_clusters.argtypes = [vp]
     L.v3d_fused_sweep_clusters.restype = i32
     L.v3d_launch_count.argtypes = [vp]
@@ -81,7 +85,8 @@ def lib():
     for name in ("v3d_create", "v3d_destroy", "v3d_split_gray", "v3d_bgr_to_gray", "v3d_unsqueeze_bgr",
                  "v3d_sgbm_compute", "v3d_set_debug_taps", "v3d_debug_tap", "v3d_debug_tap_copy", "v3d_postprocess", "v3d_normalize_u16",
                  "v3d_guided_upscale", "v3d_depth_frames", "v3d_depth_frames_host", "v3d_set_depth_scale", "v3d_png16_pack", "v3d_set_timing",
-                 "v3d_reset_timing"):
+                 "v3d_reset_timing", "v3d_depth_frames_host_async", "v3d_guided_upscale_host_async", "v3d_host_copy_only_async",
+                 "v3d_host_wait"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -304,11 +309,12 @@ class Context:
                                        _stream(depth_f32.device)), "v3d_normalize_u16")
         return out
 
-    def guided_upscale(self, depth_u16, guide_rgb, r=8, eps=1e-3, want_q=False):
+    def guided_upscale(self, depth_u16, guide_rgb, r=8, eps=1e-3, want_q=False, out=None):
         """uint16 depth [B,h,w] + RGB guide [B,gh,gw,3] -> uint16 [B,gh,gw] (definition: oracle/guided.py)."""
         B, h, w = depth_u16.shape
         _, gh, gw, _ = guide_rgb.shape
-        out = torch.empty((B, gh, gw), dtype=torch.uint16, device=depth_u16.device)
+        if out is None:
+            out = torch.empty((B, gh, gw), dtype=torch.uint16, device=depth_u16.device)
         q = torch.empty((B, gh, gw), dtype=torch.float32, device=depth_u16.device) if want_q else None
         _check(lib().v3d_guided_upscale(self._h, depth_u16.data_ptr(), w, h, guide_rgb.data_ptr(), gw, gh, B, int(r),
                                         C.c_float(eps), out.data_ptr(), q.data_ptr() if want_q else None,
@@ -342,24 +348,61 @@ class Context:
                                       C.c_float(eps), ptr("out4k"), _stream(dev)), "v3d_depth_frames")
         return res
 
-    def depth_frames_host(self, sbs_bgr, unsqueeze, guide_rgb=None, r=8, eps=1e-3, out=None):
+    def depth_frames_host(self, sbs_bgr, unsqueeze, guide_rgb=None, r=8, eps=1e-3, out=None, wait=True):
         """Same path from HOST tensors (pinned recommended); `out` maps 'disp'/'f32'/'u16'/'out4k' to
-        preallocated host tensors that receive the results.  Synchronous."""
+        preallocated host tensors that receive the results.  wait=False returns as soon as the copies and
+        kernels are enqueued (v3d_depth_frames_host_async); call host_wait() before touching the buffers."""
         if sbs_bgr.is_cuda or not sbs_bgr.is_contiguous():
             raise ValueError("sbs_bgr must be a contiguous host tensor")
         B, H, Ws, _ = sbs_bgr.shape
         out = out or {}
         gw = gh = 0
         if guide_rgb is not None:
+            if guide_rgb.is_cuda or not guide_rgb.is_contiguous():
+                raise ValueError("guide_rgb must be a contiguous host tensor")
             _, gh, gw, _ = guide_rgb.shape
 
         def ptr(k):
             return out[k].data_ptr() if k in out else None
 
+        fn = lib().v3d_depth_frames_host if wait else lib().v3d_depth_frames_host_async
         with torch.cuda.device(self.device):
-            _check(lib().v3d_depth_frames_host(self._h, sbs_bgr.data_ptr(), Ws, H, B, int(bool(unsqueeze)),
-                                               ptr("disp"), ptr("f32"), ptr("u16"),
-                                               guide_rgb.data_ptr() if guide_rgb is not None else None, gw, gh,
-                                               int(r), C.c_float(eps), ptr("out4k"), _stream(self.device)),
-                   "v3d_depth_frames_host")
+            _check(fn(self._h, sbs_bgr.data_ptr(), Ws, H, B, int(bool(unsqueeze)), ptr("disp"), ptr("f32"), ptr("u16"),
+                      guide_rgb.data_ptr() if guide_rgb is not None else None, gw, gh,
+                      int(r), C.c_float(eps), ptr("out4k"), _stream(self.device)), "v3d_depth_frames_host")
         return out
+
+    def guided_upscale_host(self, depth_u16, guide_rgb, out_u16, r=8, eps=1e-3, wait=True):
+        """The upscale step alone from HOST tensors: uint16 depth [B,H,W] (the context's eye size) + RGB guide
+        [B,gh,gw,3] -> out_u16 [B,gh,gw] (v3d_guided_upscale_host_async)."""
+        B, H, W = depth_u16.shape
+        if (W, H) != (self.W, self.H):
+            raise ValueError(f"expected depth maps of {self.W}x{self.H}, got {W}x{H}")
+        _, gh, gw, _ = guide_rgb.shape
+        with torch.cuda.device(self.device):
+            _check(lib().v3d_guided_upscale_host_async(self._h, depth_u16.data_ptr(), guide_rgb.data_ptr(), gw, gh, B, int(r),
+                                                       C.c_float(eps), out_u16.data_ptr(), _stream(self.device)),
+                   "v3d_guided_upscale_host_async")
+            if wait:
+                self.host_wait()
+        return out_u16
+
+    def host_copy_only(self, sbs_bgr=None, guide_rgb=None, out=None):
+        """Measurement aid: the host<->device copies of depth_frames_host(wait=False) without any kernel."""
+        out = out or {}
+        B = (sbs_bgr if sbs_bgr is not None else guide_rgb).shape[0]
+        H = Ws = gw = gh = 0
+        if sbs_bgr is not None:
+            _, H, Ws, _ = sbs_bgr.shape
+        if guide_rgb is not None:
+            _, gh, gw, _ = guide_rgb.shape
+        with torch.cuda.device(self.device):
+            _check(lib().v3d_host_copy_only_async(self._h, sbs_bgr.data_ptr() if sbs_bgr is not None else None, Ws, H, B,
+                                                  out["disp"].data_ptr() if "disp" in out else None,
+                                                  guide_rgb.data_ptr() if guide_rgb is not None else None, gw, gh,
+                                                  out["out4k"].data_ptr() if "out4k" in out else None,
+                                                  _stream(self.device)), "v3d_host_copy_only_async")
+
+    def host_wait(self):
+        """Sleep until the last asynchronous host call of this context has delivered its outputs."""
+        _check(lib().v3d_host_wait(self._h), "v3d_host_wait")

@@ -27,15 +27,15 @@ def _read_wav_mono(path: str):
 class VideoAligner:
     """find_alignment / assess_alignment_quality surface of align.py:13-116."""
 
-    def __init__(self, sbs_video_path: str, video_4k_path: str, work_dir: str = "temp_pipeline"):
-        self.sbs_video_path = sbs_video_path
-        self.video_4k_path = video_4k_path
+    def __init__(self, video1_path: str, video2_path: str, work_dir: str = "temp_alignment"):
+        self.video1_path = video1_path          # align.py:16-19: video 1 = the SBS clip, the time reference
+        self.video2_path = video2_path
         self.work_dir = create_work_directory(work_dir)
 
     def find_alignment(self, max_audio_length: float = 300) -> Dict:
         from scipy import signal
-        a_path = extract_audio(self.sbs_video_path, str(self.work_dir / "audio_sbs.wav"), max_duration=max_audio_length)
-        b_path = extract_audio(self.video_4k_path, str(self.work_dir / "audio_4k.wav"), max_duration=max_audio_length)
+        a_path = extract_audio(self.video1_path, self.work_dir, max_audio_length)      # align.py:41-42
+        b_path = extract_audio(self.video2_path, self.work_dir, max_audio_length)
         a, rate = _read_wav_mono(a_path)
         b, rate_b = _read_wav_mono(b_path)
         if rate != rate_b:
@@ -46,11 +46,11 @@ class VideoAligner:
         lag = int(np.argmax(corr)) - (len(a) - 1)
         peak = float(corr.max() / max(min(len(a), len(b)), 1))
         from .utils import get_video_info
-        i1, i2 = get_video_info(self.sbs_video_path) or {}, get_video_info(self.video_4k_path) or {}
+        i1, i2 = get_video_info(self.video1_path) or {}, get_video_info(self.video2_path) or {}
         fps1 = float(i1.get("fps") or 0.0)
         offset = lag / float(rate)
         # same keys as the reference's alignment_data.json (align.py:65-76)
-        data = {"video1_path": str(self.sbs_video_path), "video2_path": str(self.video_4k_path),
+        data = {"video1_path": str(self.video1_path), "video2_path": str(self.video2_path),
                 "time_offset_seconds": float(offset), "offset_frames": float(offset * fps1) if fps1 else 0.0,
                 "correlation_strength": peak, "frame_duration": (1.0 / fps1) if fps1 else 0.0,
                 "video1_fps": fps1, "video2_fps": float(i2.get("fps") or 0.0), "sample_rate": int(rate),
@@ -59,12 +59,14 @@ class VideoAligner:
             json.dump(data, f, indent=2)
         return data
 
-    def assess_alignment_quality(self, alignment_data: Dict) -> str:
+    def assess_alignment_quality(self, alignment_data: Dict, tolerance_frames: float = 2.0) -> str:
+        """align.py:87-116: same thresholds and labels."""
+        offset = float(alignment_data["time_offset_seconds"])
         c = float(alignment_data.get("correlation_strength", 0.0))
-        if c > 0.5:
-            return "excellent"
-        if c > 0.3:
-            return "good"
-        if c > 0.1:
-            return "fair"
-        return "poor"
+        if abs(offset) < float(alignment_data.get("frame_duration", 0.0)) * tolerance_frames:
+            return "EXCELLENT"
+        if c > 0.8:
+            return "GOOD"
+        if c > 0.6:
+            return "MODERATE"
+        return "POOR"

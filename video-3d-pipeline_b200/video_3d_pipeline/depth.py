@@ -59,6 +59,7 @@ class HybridStereoDepthExtractor:
         self.model_checkpoint = model_checkpoint
         self.use_neural_guidance = use_neural_guidance
         self.stereo_only = stereo_only
+        self._guidance_ignored = bool(use_neural_guidance and not stereo_only)   # asked for DPT blending, gets stereo-only
         self.unsqueeze_sbs = unsqueeze_sbs
         self.num_disparities = int(num_disparities)
         self.sgbm_mode = int(sgbm_mode)
@@ -102,7 +103,11 @@ class HybridStereoDepthExtractor:
         if self.model_loaded:
             return
         if self.use_neural_guidance and not self.stereo_only:
-            print("Neural guidance is not part of the B200 path; running stereo-only")
+            # the reference would blend 0.7 * stereo + 0.3 * DPT here (depth.py:344-371): results equal the
+            # reference's only in its stereo-only mode (stereo_only=True / --no-neural, or no checkpoint)
+            import sys
+            print("Warning: neural guidance requested but not part of the B200 path; running stereo-only "
+                  "(results match the reference's stereo-only mode)", file=sys.stderr)
         self.stereo_only = True
         self.model_loaded = True
 
@@ -125,9 +130,16 @@ class HybridStereoDepthExtractor:
 
     # ------------------------------------------------------------------ cache (depth.py:116-140)
     def get_cache_path(self, video_path: str, frame_start: int, frame_count: int) -> Path:
+        # depth.py:118 verbatim; everything that changes the pixels without being part of the reference's key is
+        # appended only when it differs from the reference's behaviour, so a reference-equivalent run keeps its hash
         key = f"{video_path}_{frame_start}_{frame_count}_{self.model_checkpoint}_{self.unsqueeze_sbs}"
-        if getattr(self, "depth_scale", "frame") != "frame":      # the reference key (depth.py:118) stays as is for reference behaviour
-            key += f"_{self.depth_scale}{self.num_disparities}"
+        nd, mode = getattr(self, "num_disparities", 64), getattr(self, "sgbm_mode", _native.MODE_SGBM)
+        if nd != 64 or mode != _native.MODE_SGBM:                 # depth.py:317 / cv2 default mode
+            key += f"_D{nd}m{mode}"
+        if getattr(self, "depth_scale", "frame") != "frame":
+            key += f"_{self.depth_scale}{nd}"
+        if getattr(self, "_guidance_ignored", False):             # never share a directory with DPT-blended maps
+            key += "_stereo"
         sub = self.cache_dir / f"depth_{hashlib.md5(key.encode()).hexdigest()[:16]}"
         sub.mkdir(exist_ok=True)
         return sub
@@ -154,7 +166,8 @@ class HybridStereoDepthExtractor:
         if not cap.isOpened():
             raise ValueError(f"Could not open video file: {video_path}")      # depth.py:164-165
         try:
-            cap.set(cv2.CAP_PROP_POS_FRAMES, start_frame)                      # depth.py:168
+            if start_frame > 0:
+                cap.set(cv2.CAP_PROP_POS_FRAMES, start_frame)                  # depth.py:168
             for _ in range(count):
                 ok, frame = cap.read()
                 if not ok:
@@ -162,6 +175,43 @@ class HybridStereoDepthExtractor:
                 yield frame
         finally:
             cap.release()
+
+    # codecs whose every frame is a key frame: a seek lands exactly on the requested frame
+    _INTRA_FOURCC = {"mjpg", "jpeg", "mjpa", "mjpb", "mjls", "ffv1", "hfyu", "ffvh", "png ", "mpng", "raw ", "dib ",
+                     "yuy2", "i420", "iyuv", "uyvy", "v210", "r210", "apch", "apcn", "apcs", "apco", "ap4h", "ap4x",
+                     "avdn", "avdh", "dvsd", "dvhd", "dv25", "dv50", "ulrg", "ulry", "ulh0", "ulh2", "cfhd"}
+
+    @classmethod
+    def seek_is_frame_exact(cls, video_path: str) -> bool:
+        """True when cv2.VideoCapture.set(CAP_PROP_POS_FRAMES, n) is known to land on frame n: intra-only codecs.
+        Long-GOP / B-frame / VFR streams (H.264, HEVC, MPEG-4 ...) are not, so they are read by ONE sequential
+        reader exactly like the reference (depth.py:168-177)."""
+        cap = cv2.VideoCapture(video_path)
+        try:
+            if not cap.isOpened():
+                return False
+            v = int(cap.get(cv2.CAP_PROP_FOURCC))
+        finally:
+            cap.release()
+        fourcc = "".join(chr((v >> (8 * i)) & 0xFF) for i in range(4)).lower()
+        return fourcc in cls._INTRA_FOURCC
+
+    @staticmethod
+    def plan_reader_slices(first_frame: int, count: int, batch: int, readers: int, index_base: int = 0):
+        """Contiguous (first frame, frame count, first output index) slices, whole batches each, for `readers`
+        decode threads."""
+        nb_total = (count + batch - 1) // batch
+        readers = max(1, min(int(readers), nb_total))
+        slices = []
+        base, extra = divmod(nb_total, readers)
+        at = 0
+        for k in range(readers):
+            nb = base + (1 if k < extra else 0)
+            n = min(nb * batch, count - at)
+            if n > 0:
+                slices.append((first_frame + at, n, index_base + at))
+            at += n
+        return slices
 
     def extract_frames_opencv(self, video_path: str, start_frame: int = 0, max_frames: int = None) -> List[np.ndarray]:
         """depth.py:142-188 (kept for API compatibility; process_video_sbs streams instead)."""
@@ -294,32 +344,31 @@ class HybridStereoDepthExtractor:
         import queue
         import threading
         bs = max(1, self.batch_size)
-        n_readers = max(1, min(int(self.decode_threads), (count + bs - 1) // bs))
-        slices = []                                    # (first frame, frame count, first output index)
-        base, extra = divmod((count + bs - 1) // bs, n_readers)
-        at = 0
-        for k in range(n_readers):
-            nb = base + (1 if k < extra else 0)
-            n = min(nb * bs, count - at)
-            if n > 0:
-                slices.append((first_frame + at, n, index_base + at))
-            at += n
+        # several readers only where seeking is frame-exact; otherwise one sequential reader, as the reference does
+        readers = int(self.decode_threads) if self.seek_is_frame_exact(video_path) else 1
+        slices = self.plan_reader_slices(first_frame, count, bs, readers, index_base)
         q: "queue.Queue" = queue.Queue(maxsize=2 * len(slices))
         stop = threading.Event()
 
         def reader(start: int, n: int, out_index: int):
             try:
                 batch: List[np.ndarray] = []
+                got = 0
                 for frame in self._iter_frames(video_path, start, n):
                     if stop.is_set():
                         return
                     batch.append(frame)
+                    got += 1
                     if len(batch) == bs:
                         q.put((out_index, batch))
                         out_index += len(batch)
                         batch = []
                 if batch:
                     q.put((out_index, batch))
+                # a short read anywhere but at the end of the clip would leave a hole in the depth_%06d numbering
+                if got < n and start + n < first_frame + count:
+                    raise RuntimeError(f"Frame extraction failed: frames {start + got}..{start + n - 1} of {video_path} "
+                                       "could not be decoded")
             except BaseException as e:                 # surfaces in the consumer
                 q.put(e)
             finally:

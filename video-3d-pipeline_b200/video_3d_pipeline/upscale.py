@@ -96,8 +96,13 @@ class SimpleDepthUpscaler:
         n_batches = (len(depth_files) + self.batch_size - 1) // self.batch_size
         # the preview video needs frames in order, so it keeps one reader; otherwise the clip is cut into
         # contiguous slices, one reader (own VideoCapture, seeked to its first frame) each
-        n_readers = 1 if writer is not None else max(1, min(self.decode_threads, n_batches))
+        # ... and only where a seek lands exactly on the requested frame (intra-only codecs); long-GOP guides are
+        # read by one sequential reader
+        from .depth import HybridStereoDepthExtractor
+        exact = guide_video is None or HybridStereoDepthExtractor.seek_is_frame_exact(str(guide_video))
+        n_readers = 1 if (writer is not None or not exact) else max(1, min(self.decode_threads, n_batches))
         batches: "queue.Queue" = queue.Queue(maxsize=2 * n_readers + 1)
+        stop = threading.Event()
 
         def read_depth(f):
             d = cv2.imread(f, cv2.IMREAD_UNCHANGED)
@@ -115,6 +120,8 @@ class SimpleDepthUpscaler:
                     if first > 0:
                         cap.set(cv2.CAP_PROP_POS_FRAMES, first)
                 for bi in range(b0, b1):
+                    if stop.is_set():
+                        return
                     s0 = bi * self.batch_size
                     files = depth_files[s0:s0 + self.batch_size]
                     maps = list(pool.map(read_depth, files))
@@ -188,6 +195,7 @@ class SimpleDepthUpscaler:
             for f in pending:
                 f.result()
         finally:
+            stop.set()                                  # after an error the producers stop at their next batch
             while any(t.is_alive() for t in prods):     # unblock producers stuck on a full queue
                 try:
                     batches.get_nowait()
@@ -198,10 +206,34 @@ class SimpleDepthUpscaler:
             pool.shutdown(wait=True)
             if writer is not None:
                 writer.release()
-        if not out_path.exists():          # no encoder in this OpenCV build: leave a pointer file
-            out_path.write_text(f"16-bit PNG sequence: {png_dir}\n")
-        print(f"✓ Depth video saved: {output_path}  (16-bit frames: {png_dir})")
-        return output_path
+        # what was produced is recorded next to the requested path; the 16-bit PNG sequence is the product, the mp4
+        # only an 8-bit preview (and absent when preview=False or this OpenCV build has no encoder)
+        import json
+        have_video = out_path.exists() and out_path.stat().st_size > 0
+        self._sidecar(out_path).write_text(json.dumps({"png16_dir": str(png_dir), "frames": len(depth_files),
+                                                       "width": int(target_width), "height": int(target_height),
+                                                       "preview_video": str(out_path) if have_video else None}) + "\n")
+        print(f"✓ Depth frames saved: {png_dir}" + (f"  (8-bit preview: {output_path})" if have_video else ""))
+        return output_path if have_video else str(png_dir)
+
+    @staticmethod
+    def _sidecar(out_path: Path) -> Path:
+        return out_path.with_suffix(out_path.suffix + ".json")
+
+    def _already_processed(self, out_path: Path, n_expected: int):
+        """The finished result of an earlier run: its sidecar exists and the PNG sequence is complete."""
+        import json
+        try:
+            meta = json.loads(self._sidecar(out_path).read_text())
+        except (OSError, ValueError):
+            return None
+        png_dir = Path(meta.get("png16_dir", ""))
+        if meta.get("frames") != n_expected or not png_dir.is_dir():
+            return None
+        if len(list(png_dir.glob("depth4k_*.png"))) < n_expected:
+            return None
+        pv = meta.get("preview_video")
+        return pv if pv and Path(pv).exists() else str(png_dir)
 
     def process_depth_upscaling(self, depth_dir: str, video_4k_path: str, output_path: str = None,
                                 force_reprocess: bool = False) -> str:
@@ -217,9 +249,12 @@ class SimpleDepthUpscaler:
         if output_path is None:
             output_path = f"depth_4k_{Path(depth_dir).name}.mp4"               # upscale.py:98-100
         output_path = Path(output_path)
-        if output_path.exists() and not force_reprocess:                      # upscale.py:104-107
-            print(f"✓ Using existing depth video: {output_path}")
-            return str(output_path)
+        if not force_reprocess:                                               # upscale.py:104-107
+            n_maps = len(glob.glob(os.path.join(str(depth_dir), "depth_*.png")))
+            done = self._already_processed(output_path, n_maps) if n_maps else None
+            if done:
+                print(f"✓ Using existing depth video: {done}")
+                return done
         # the alignment step leaves alignment_data.json in the work dir, next to the depth cache (run_pipeline.py:53)
         start = 0
         align_json = Path(depth_dir).parent / "alignment_data.json"

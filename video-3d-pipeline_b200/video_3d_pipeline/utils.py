@@ -98,18 +98,30 @@ def verify_video_compatibility(video1_path: str, video2_path: str) -> Dict:
     }
 
 
-def extract_audio(video_path: str, output_path: str = None, sample_rate: int = 22050, max_duration: float = None) -> str:
-    """Mono WAV extraction for the alignment step (utils.py:41-119 surface).  Needs the ffmpeg binary."""
+def extract_audio(video_path: str, work_dir: Path, duration_seconds: float = 600, sample_rate: int = 22050) -> str:
+    """Mono WAV extraction for the alignment step, cached in work_dir (utils.py:41-119: same positional
+    signature, cache file name and ValueError sites).  Needs the ffmpeg binary."""
+    import hashlib
+    import os
     exe = shutil.which("ffmpeg")
     if exe is None:
         raise RuntimeError("extract_audio needs the ffmpeg binary, which is not installed; "
                            "audio alignment is outside the accelerated depth path")
-    output_path = output_path or str(Path(video_path).with_suffix(".wav"))
-    cmd = [exe, "-y", "-v", "error", "-i", str(video_path), "-vn", "-ac", "1", "-ar", str(sample_rate)]
-    if max_duration:
-        cmd += ["-t", str(max_duration)]
-    subprocess.run(cmd + [output_path], check=True)
-    return output_path
+    if not get_video_info(video_path):
+        raise ValueError(f"Could not read video info for {video_path}")       # utils.py:47-49
+    video_hash = hashlib.md5(f"{video_path}_{duration_seconds}_{sample_rate}".encode()).hexdigest()[:16]
+    wav = Path(work_dir) / f"audio_cache_{video_hash}.wav"                      # utils.py:63-64
+    if wav.exists() and os.path.getmtime(wav) > os.path.getmtime(video_path):   # utils.py:67-72
+        print(f"Using cached audio: {wav}")
+        return str(wav)
+    cmd = [exe, "-y", "-v", "error", "-t", str(duration_seconds), "-i", str(video_path), "-vn", "-acodec", "pcm_s16le",
+           "-ac", "1", "-ar", str(sample_rate), str(wav)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0 or not wav.exists():
+        raise ValueError(f"Could not extract audio from {video_path}")         # utils.py:105, 108
+    if wav.stat().st_size < 1000:
+        raise ValueError("Audio extraction produced unusually small file")     # utils.py:112-113
+    return str(wav)
 
 
 def apply_alignment_offset(alignment_file: str, target_video_path: str, base_start_time: float = 0) -> float:
