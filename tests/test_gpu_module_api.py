@@ -175,6 +175,19 @@ def test_upscale_module_pixels_with_alignment_offset(tmp_path):
         assert again == res
         if kw:
             assert not out.exists() and Path(res).is_dir()        # preview=False: no fake .mp4
+    # single-file 16-bit output: lossless FFV1 gray16, frame for frame the PNG sequence
+    out = tmp_path / "o16.mp4"
+    SimpleDepthUpscaler(use_nvenc=True, batch_size=2, preview=False, video16=True).process_depth_upscaling(
+        str(ddir), str(gclip), output_path=str(out))
+    cap = cv2.VideoCapture(str(tmp_path / "o16_16bit.mkv"), cv2.CAP_FFMPEG, [cv2.CAP_PROP_CONVERT_RGB, 0])
+    pngs = sorted((tmp_path / "o16_png16").glob("depth4k_*.png"))
+    assert len(pngs) == n
+    for p in pngs:
+        ok, f = cap.read()
+        assert ok and f.dtype == np.uint16
+        assert np.array_equal(f.reshape(2 * h, 2 * w), cv2.imread(str(p), cv2.IMREAD_UNCHANGED))
+    assert not cap.read()[0]
+    cap.release()
 
 
 def _run_pipeline_calls(sbs_video, video_4k, work_dir, max_frames):

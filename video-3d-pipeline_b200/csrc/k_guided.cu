@@ -69,6 +69,11 @@ __host__ __device__ constexpr int row_pitch()
     return vp;
 }
 
+// The coefficient kernel's horizontal pass splits every run of 8 outputs over a lane pair when it can (radius 8,
+// one row of the group per warp).
+template <int RT, int NT, int R, int GR>
+__host__ __device__ constexpr bool paired_pass() { return RT == 8 && GR == 8 && NT == 32 * R; }
+
 // shared-memory bytes of k_guided_coeff_s
 template <int RT, int NT, int R, int GR>
 constexpr size_t coeff_s_smem(int win)
@@ -225,7 +230,96 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
         __syncthreads();
         stage_rows(g + 1);                                           // lands while the horizontal pass runs
 
-        // horizontal pass + 3x3 solve: item = (row of the group, run of GR output columns)
+        // horizontal pass + 3x3 solve
+        const float kn = k255 * inv_n, kkn = k255 * k255 * inv_n;
+        const float cI0 = (float)(crgb & 0xff) * k255 - 0.5f, cI1 = (float)((crgb >> 8) & 0xff) * k255 - 0.5f,
+                    cI2 = (float)((crgb >> 16) & 0xff) * k255 - 0.5f;
+        // window sums acc[13] of one output pixel -> (a0, a1, a2, b)
+        auto solve = [&](const float (&acc)[13]) -> float4 {
+            const float mI0 = acc[0] * kn, mI1 = acc[1] * kn, mI2 = acc[2] * kn, mp = acc[3] * inv_n;
+            const float c0 = acc[4] * kn - mI0 * mp, c1 = acc[5] * kn - mI1 * mp, c2 = acc[6] * kn - mI2 * mp;
+            const float s00 = acc[7] * kkn - mI0 * mI0 + eps, s01 = acc[8] * kkn - mI0 * mI1, s02 = acc[9] * kkn - mI0 * mI2;
+            const float s11 = acc[10] * kkn - mI1 * mI1 + eps, s12 = acc[11] * kkn - mI1 * mI2, s22 = acc[12] * kkn - mI2 * mI2 + eps;
+            // (Sigma + eps I) a = cov(I, p) by LDL^T: the matrix is symmetric positive definite (pivots >= eps)
+            // and for nearly collinear colour channels -- the usual case -- this stays accurate where the
+            // adjugate / determinant form loses digits like (lambda_max / eps)^2.  Reciprocals: approx + one
+            // Newton step (~1 ulp).
+            auto rcp = [](float x) -> float {
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+                return r * fmaf(-x, r, 2.0f);
+            };
+            const float i0 = rcp(s00);
+            const float l1 = s01 * i0, l2 = s02 * i0;
+            const float d1 = fmaf(-l1, s01, s11), e1 = fmaf(-l1, s02, s12);
+            const float i1 = rcp(d1);
+            const float l21 = e1 * i1;
+            const float d2 = fmaf(-l21, e1, fmaf(-l2, s02, s22));
+            const float i2 = rcp(d2);
+            const float y1 = fmaf(-l1, c0, c1);
+            const float y2 = fmaf(-l21, y1, fmaf(-l2, c0, c2));
+            const float a2 = y2 * i2;
+            const float a1 = fmaf(-l21, a2, y1 * i1);
+            const float a0 = fmaf(-l2, a2, fmaf(-l1, a1, c0 * i0));
+            // b referred to a guide centred at 0.5:  q = a.(I - 0.5) + b
+            const float bb = (mp + cp) - a0 * (mI0 + cI0) - a1 * (mI1 + cI1) - a2 * (mI2 + cI2);
+            return make_float4(a0, a1, a2, bb);
+        };
+        if constexpr (paired_pass<RT, NT, R, GR>()) {
+            // One row of the group per warp; lanes l and l + 16 share a run of 8 outputs (4 each).  Their two first windows
+            // (17 columns, 4 apart) overlap in 13 columns: each lane sums half of the overlap plus its own 4 columns, the
+            // halves are exchanged with one shuffle per plane, then each lane slides its window over its 4 outputs.
+            // 28 of 32 lanes work, against 56 of 128 threads when one thread owns a whole run.
+            const int lane = tid & 31, jj = tid >> 5;
+            const int o = g * R + jj - 2 * RT;                      // output row of this warp in this group (warp-uniform)
+            if (o >= 0 && o < seg_h) {
+                const int half = lane >> 4, run_raw = lane & 15;
+                const int run = min(run_raw, runs - 1), xb = run * GR;      // lanes past the last run repeat it, store nothing
+                const float4* vr = vbuf + jj * VP + xb + run;           // slot of the run's first column
+                const float* vs = v12 + jj * VP + xb + run;
+                float acc[13], part[13], m[13];
+                auto ld13 = [&](int da, int db) {                       // column offset from the run start: da (lanes 0..15), db (16..31)
+                    const int e = half ? db + db / GR : da + da / GR;
+                    const float4 g0 = vr[e], g1 = vr[e + R * VP], g2 = vr[e + 2 * R * VP];
+                    m[0] = g0.x; m[1] = g0.y; m[2] = g0.z; m[3] = g0.w;
+                    m[4] = g1.x; m[5] = g1.y; m[6] = g1.z; m[7] = g1.w;
+                    m[8] = g2.x; m[9] = g2.y; m[10] = g2.z; m[11] = g2.w;
+                    m[12] = vs[e];
+                };
+#pragma unroll
+                for (int q = 0; q < 13; q++) { acc[q] = 0.0f; part[q] = 0.0f; }
+#pragma unroll
+                for (int t = 0; t < 4; t++) {                           // own columns: 0..3 / 17..20
+                    ld13(t, 17 + t);
+#pragma unroll
+                    for (int q = 0; q < 13; q++) acc[q] += m[q];
+                }
+#pragma unroll
+                for (int t = 0; t < 7; t++) {                           // half of the shared columns: 4..10 / 11..16
+                    ld13(4 + t, t < 6 ? 11 + t : 11);
+#pragma unroll
+                    for (int q = 0; q < 13; q++) part[q] += (t == 6 && half) ? 0.0f : m[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 13; q++) acc[q] += part[q] + __shfl_xor_sync(0xffffffffu, part[q], 16);
+                const size_t orow = (size_t)(Y0 + o) * gw;
+#pragma unroll
+                for (int o2 = 0; o2 < 4; o2++) {
+                    if (o2 > 0) {
+                        ld13(o2 + 2 * RT, 4 + o2 + 2 * RT);
+#pragma unroll
+                        for (int q = 0; q < 13; q++) acc[q] += m[q];
+                        ld13(o2 - 1, 4 + o2 - 1);
+#pragma unroll
+                        for (int q = 0; q < 13; q++) acc[q] -= m[q];
+                    }
+                    const int X = X0 + xb + 4 * half + o2;
+                    const float4 c4 = solve(acc);
+                    if (run_raw < runs && X < gw) ab[orow + X] = c4;
+                }
+            }
+        } else {
+        // item = (row of the group, run of GR output columns)
         for (int it = tid; it < R * runs; it += NT) {
             const int jj = it / runs, run = it - jj * runs;
             const int o = g * R + jj - 2 * r;
@@ -273,9 +367,6 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
                 }
             }
             const size_t orow = (size_t)(Y0 + o) * gw;
-            const float kn = k255 * inv_n, kkn = k255 * k255 * inv_n;
-            const float cI0 = (float)(crgb & 0xff) * k255 - 0.5f, cI1 = (float)((crgb >> 8) & 0xff) * k255 - 0.5f,
-                        cI2 = (float)((crgb >> 16) & 0xff) * k255 - 0.5f;
 #pragma unroll
             for (int o2 = 0; o2 < GR; o2++) {
                 if (o2 > 0) {
@@ -288,35 +379,9 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
                 }
                 const int X = X0 + xb + o2;
                 if (X >= gw) break;
-                const float mI0 = acc[0] * kn, mI1 = acc[1] * kn, mI2 = acc[2] * kn, mp = acc[3] * inv_n;
-                const float c0 = acc[4] * kn - mI0 * mp, c1 = acc[5] * kn - mI1 * mp, c2 = acc[6] * kn - mI2 * mp;
-                const float s00 = acc[7] * kkn - mI0 * mI0 + eps, s01 = acc[8] * kkn - mI0 * mI1, s02 = acc[9] * kkn - mI0 * mI2;
-                const float s11 = acc[10] * kkn - mI1 * mI1 + eps, s12 = acc[11] * kkn - mI1 * mI2, s22 = acc[12] * kkn - mI2 * mI2 + eps;
-                // (Sigma + eps I) a = cov(I, p) by LDL^T: the matrix is symmetric positive definite (pivots >= eps)
-                // and for nearly collinear colour channels -- the usual case -- this stays accurate where the
-                // adjugate / determinant form loses digits like (lambda_max / eps)^2.  Reciprocals: approx + one
-                // Newton step (~1 ulp).
-                auto rcp = [](float x) -> float {
-                    float r;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-                    return r * fmaf(-x, r, 2.0f);
-                };
-                const float i0 = rcp(s00);
-                const float l1 = s01 * i0, l2 = s02 * i0;
-                const float d1 = fmaf(-l1, s01, s11), e1 = fmaf(-l1, s02, s12);
-                const float i1 = rcp(d1);
-                const float l21 = e1 * i1;
-                const float d2 = fmaf(-l21, e1, fmaf(-l2, s02, s22));
-                const float i2 = rcp(d2);
-                const float y1 = fmaf(-l1, c0, c1);
-                const float y2 = fmaf(-l21, y1, fmaf(-l2, c0, c2));
-                const float a2 = y2 * i2;
-                const float a1 = fmaf(-l21, a2, y1 * i1);
-                const float a0 = fmaf(-l2, a2, fmaf(-l1, a1, c0 * i0));
-                // b referred to a guide centred at 0.5:  q = a.(I - 0.5) + b
-                const float bb = (mp + cp) - a0 * (mI0 + cI0) - a1 * (mI1 + cI1) - a2 * (mI2 + cI2);
-                ab[orow + X] = make_float4(a0, a1, a2, bb);
+                ab[orow + X] = solve(acc);
             }
+        }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();

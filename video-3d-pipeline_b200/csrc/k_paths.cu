@@ -158,13 +158,17 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     uint64_t* my_bar = mb + w;
     const uint32_t rx_bytes = ((has_left ? 1u : 0u) + (has_right ? 1u : 0u)) * 32u * (uint32_t)sizeof(VT);
     uint32_t to_l = 0, to_l_bar = 0, to_r = 0, to_r_bar = 0;      // cluster addresses in the neighbours' shared memory
+    V3D_DASSERT(rank >= 0 && rank < V3_CL && (int)cluster.num_blocks() == V3_CL);
+    V3D_DASSERT(nv == 0 || (gcol0 < W1 && gcol0 + nv <= W1));
     if (has_left) {
         const int nr = w > 0 ? rank : rank - 1, nw = w > 0 ? w - 1 : V3_NW - 1;
+        V3D_DASSERT(nr >= 0 && nr < V3_CL && nw >= 0 && nw < V3_NW);      // the left neighbour's inbox slot exists
         to_l = mapa_u32(smem_u32(inbox + (nw * 2 + 1) * 32 + lane), nr);
         to_l_bar = mapa_u32(smem_u32(mb + nw), nr);
     }
     if (has_right) {
         const int nr = w < V3_NW - 1 ? rank : rank + 1, nw = w < V3_NW - 1 ? w + 1 : 0;
+        V3D_DASSERT(nr >= 0 && nr < V3_CL && nw >= 0 && nw < V3_NW);      // a column to the right implies a CTA / warp to the right
         to_r = mapa_u32(smem_u32(inbox + (nw * 2 + 0) * 32 + lane), nr);
         to_r_bar = mapa_u32(smem_u32(mb + nw), nr);
     }
@@ -216,6 +220,8 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
         const VT* Snext = S + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
         const uint32_t phase = (i >> 1) & 1;
+        V3D_DASSERT(par == 0 || par == 1);                               // double-buffered inboxes: [par][warp][side]
+        V3D_DASSERT((char*)(in_r + par * PARSTRIDE) + sizeof(VT) <= (char*)mb && y >= 0 && y < H);
         if (has_right) st_async(to_r + par * PARSTRIDE * (uint32_t)sizeof(VT), Ml[(CPW - 1) * 32], to_r_bar + par * V3_NW * 8);
         if (has_left) st_async(to_l + par * PARSTRIDE * (uint32_t)sizeof(VT), Mr[0], to_l_bar + par * V3_NW * 8);
         if (lane == 0 && rx_bytes) mbar_expect_tx(my_bar + par * V3_NW, rx_bytes);

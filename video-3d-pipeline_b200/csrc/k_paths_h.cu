@@ -14,6 +14,9 @@ namespace {
 
 constexpr int HW_WARPS = 8;   // warps (rows) per block
 constexpr int CH = 8;         // pixel steps per staged chunk
+#ifndef V3D_WTA_NST
+#define V3D_WTA_NST 2       // staged chunks per warp of the last path kernel (2: three blocks per SM; 3 measured 3 % slower)
+#endif
 
 // ------------------------------------------------------------------------------------------
 // left -> right (predecessor x-1), CHECKPOINT pass.  The left-to-right costs L are never written: this kernel
@@ -121,7 +124,7 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
 {
     using VT = typename Vec<NR>::T;
     constexpr int D = 64 * NR;
-    constexpr int NST = 3;
+    constexpr int NST = V3D_WTA_NST;
     constexpr int STEP_B = 128 * NR;
     constexpr int NU = 2 * NR;                   // uint4 (8 disparities each) per lane in the WTA phase
     static_assert(CH == 8, "the WTA lane mapping assumes 8 pixels per chunk");
@@ -163,9 +166,9 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
         if (lo > 0) bulk_g2s(kst + st * STEP_B, Kg + (size_t)c * STEP_B, STEP_B, &bars[wib][st]);   // the left-most chunk starts a path
     };
     if (lane == 0) {
-        issue(0);
-        if (nchunks > 1) issue(1);
-        if (nchunks > 2) issue(2);
+#pragma unroll
+        for (int s = 0; s < NST; s++)
+            if (s < nchunks) issue(s);
     }
     uint32_t M[NR];
 #pragma unroll
@@ -297,7 +300,7 @@ int launch_wta(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
 {
     const int rows = batch * ctx->H;
     const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
-    const size_t smem = (size_t)HW_WARPS * (2 * CH + 1) * 3 * 128 * NR;
+    const size_t smem = (size_t)HW_WARPS * (2 * CH + 1) * V3D_WTA_NST * 128 * NR;
     dim3 grid((rows + HW_WARPS - 1) / HW_WARPS), block(HW_WARPS * 32);
     const bool pad = ctx->D != ctx->Dk;
     auto wta = tap_s ? (pad ? k_path_rl_wta_tma<NR, true, true> : k_path_rl_wta_tma<NR, true, false>)

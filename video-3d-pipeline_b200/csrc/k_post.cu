@@ -167,8 +167,10 @@ __host__ inline bool vec8_ok(const void* p, size_t pitch_e, size_t stride_e, int
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int uf_find(const int* L, int i)
 {
+    V3D_DASSERT(i >= 0);
     int p = L[i];
-    while (p != i) { i = p; p = L[i]; }
+    // parents only ever decrease (atomicMin), so a chain is strictly descending: it cannot cycle or leave the frame upwards
+    while (p != i) { V3D_DASSERT(p >= 0 && p < i); i = p; p = L[i]; }
     return i;
 }
 
@@ -178,8 +180,8 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b)
     do {
         a = uf_find(L, a);
         b = uf_find(L, b);
-        if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
-        else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        if (a < b) { const int old = atomicMin(&L[b], a); V3D_DASSERT(old >= 0 && old <= b); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(&L[a], b); V3D_DASSERT(old >= 0 && old <= a); done = (old == a); a = old; }
         else done = true;
     } while (!done);
 }

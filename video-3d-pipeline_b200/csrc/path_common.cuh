@@ -24,6 +24,9 @@ template <> __device__ __forceinline__ uint4 pack<4>(const uint32_t (&r)[4]) { r
 #ifndef V3D_STEP_MIN3
 #define V3D_STEP_MIN3 1
 #endif
+#ifndef V3D_STEP_UNEG
+#define V3D_STEP_UNEG 0      // measured slower: the path kernels are issue-bound, not only integer-pipe-bound
+#endif
 template <int NR>
 __device__ __forceinline__ void path_step(uint32_t (&M)[NR], const uint32_t (&C)[NR], uint32_t (&L)[NR],
                                           uint32_t P1p, uint32_t P2p, int lane)
@@ -57,9 +60,20 @@ __device__ __forceinline__ void path_step(uint32_t (&M)[NR], const uint32_t (&C)
 #endif
         m = __vminu2(m, L[k]);
     }
+#if V3D_STEP_UNEG
+    // The warp minimum and its negation stay off the half-rate integer pipe: the lane's smaller half is moved into
+    // the HIGH half with a multiply (FMA pipe), CREDUX leaves (min << 16) in a uniform register, and -min in both
+    // halves comes from a negate, a multiply-high and an add, all IMAD forms (3 integer-pipe instructions fewer per
+    // step than PRMT + VIMNMX ... LOP3 + VIADD.16x2).
+    m = __vminu2(m, m * 0x10000u);                           // high half = min(hi, lo); low half = 0
+    const uint32_t r = __reduce_min_sync(V3D_FULL_MASK, m);  // = min_d L << 16
+    const uint32_t x = 0u - r;                               // (-min & 0xffff) << 16
+    const uint32_t neg = x + __umulhi(x, 0x10001u);          // + (x >> 16) as a multiply-high: -min in both halves
+#else
     m = __vminu2(m, __byte_perm(m, 0, 0x1032));          // both halves = this lane's minimum
     const uint32_t mm = __reduce_min_sync(V3D_FULL_MASK, m);
     const uint32_t neg = __vadd2(~mm, 0x00010001u);       // -min in both halves
+#endif
 #pragma unroll
     for (int k = 0; k < NR; k++) M[k] = __viaddmin_s16x2(L[k], neg, P2p);
 }

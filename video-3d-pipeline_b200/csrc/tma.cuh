@@ -1,6 +1,9 @@
 // Inline-PTX wrappers for mbarrier + cp.async.bulk (TMA bulk copies; SASS: UBLKCP, SYNCS).
 #pragma once
 #include <stdint.h>
+#ifdef V3D_DEBUG_ASSERTS
+#include <stdio.h>
+#endif
 
 namespace {
 
@@ -16,6 +19,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
+#ifdef V3D_DEBUG_ASSERTS
+    // debug build: a wait that never completes (a lost arrival / transaction count) traps instead of hanging the GPU
+    for (long long spin = 0;; spin++) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1ll << 26)) { printf("V3D_DASSERT failed: mbarrier wait timed out, block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x); __trap(); }
+    }
+#endif
     asm volatile(
         "{\n"
         ".reg .pred p;\n"

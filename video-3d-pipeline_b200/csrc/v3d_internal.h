@@ -8,6 +8,17 @@
 
 #define V3D_FULL_MASK 0xffffffffu
 
+// Debug build (-DV3D_DEBUG_ASSERTS=1, `V3D_NVCC_EXTRA=-DV3D_DEBUG_ASSERTS=1 python build.py`): index and protocol
+// checks in the code that synchronises without locks -- the neighbour inboxes / mbarrier ring of the fused vertical
+// sweep and the union-find forest of the speckle filter -- trap instead of corrupting memory (compute-sanitizer is
+// not usable on every GPU pool).  tools/gpu_debug_asserts.sh runs the parity tests against such a build.
+#ifdef V3D_DEBUG_ASSERTS
+#include <stdio.h>
+#define V3D_DASSERT(c) do { if (!(c)) { printf("V3D_DASSERT failed: %s (%s:%d) block %d thread %d\n", #c, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define V3D_DASSERT(c) ((void)0)
+#endif
+
 enum V3dStage {
     ST_SPLIT_GRAY = 0, ST_PREFILTER, ST_COST, ST_PATHS, ST_LR, ST_WTA, ST_SELECT, ST_MEDIAN,
     ST_SPECKLE, ST_POST, ST_GUIDED, ST_GUIDED_APPLY, ST_COPY, ST_COUNT

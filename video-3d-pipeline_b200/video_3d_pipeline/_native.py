@@ -10,7 +10,10 @@ from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "libv3d.so"
+import os
+
+# V3D_LIB points at another build of the same library (A/B measurements of kernel variants); default: in-tree
+_LIB_PATH = Path(os.environ.get("V3D_LIB") or (Path(__file__).resolve().parent / "libv3d.so"))
 _lib = None
 
 V3D_EINVAL, V3D_ENOMEM, V3D_ECUDA, V3D_ESTATE = -1, -2, -3, -4

@@ -26,7 +26,7 @@ class SimpleDepthUpscaler:
 
     def __init__(self, use_nvenc: bool = True, radius: int = 8, eps: float = 1e-3, batch_size: int = 4,
                  gpu_index: int = 0, png_compression: int = 1, png_threads: int = 6, preview: bool = True,
-                 decode_threads: int = 4):
+                 decode_threads: int = 4, video16: bool = False):
         self.use_nvenc = use_nvenc          # kept for signature compatibility (upscale.py:15-16)
         self.radius = int(radius)
         self.eps = float(eps)
@@ -37,6 +37,9 @@ class SimpleDepthUpscaler:
         self.png_compression = int(png_compression)
         self.png_threads = max(1, int(png_threads))
         self.preview = bool(preview)        # also write the 8-bit mp4 preview at output_path
+        # also write ONE 16-bit video file next to output_path: <stem>_16bit.mkv, FFV1 (lossless) gray16le -- the
+        # single-file 16-bit form of step 3's output (the reference's H.264, upscale.py:53-59, keeps 8 bits)
+        self.video16 = bool(video16)
         self.decode_threads = max(1, int(decode_threads))   # guide-video readers, each on a contiguous slice of the clip
         if not torch.cuda.is_available():
             raise RuntimeError("CUDA not available but requested")
@@ -78,6 +81,13 @@ class SimpleDepthUpscaler:
                                      (int(target_width), int(target_height)), False)
             if not writer.isOpened():
                 writer = None
+        writer16, path16 = None, out_path.with_name(out_path.stem + "_16bit.mkv")
+        if self.video16:
+            writer16 = cv2.VideoWriter(str(path16), cv2.CAP_FFMPEG, cv2.VideoWriter_fourcc(*"FFV1"), float(fps),
+                                       (int(target_width), int(target_height)),
+                                       [cv2.VIDEOWRITER_PROP_DEPTH, cv2.CV_16U, cv2.VIDEOWRITER_PROP_IS_COLOR, 0])
+            if not writer16.isOpened():
+                raise RuntimeError("this OpenCV build cannot write 16-bit FFV1 video (video16=True)")
 
         if guide_video is not None:
             probe = cv2.VideoCapture(str(guide_video))
@@ -100,7 +110,7 @@ class SimpleDepthUpscaler:
         # read by one sequential reader
         from .depth import HybridStereoDepthExtractor
         exact = guide_video is None or HybridStereoDepthExtractor.seek_is_frame_exact(str(guide_video))
-        n_readers = 1 if (writer is not None or not exact) else max(1, min(self.decode_threads, n_batches))
+        n_readers = 1 if (writer is not None or writer16 is not None or not exact) else max(1, min(self.decode_threads, n_batches))
         batches: "queue.Queue" = queue.Queue(maxsize=2 * n_readers + 1)
         stop = threading.Event()
 
@@ -192,6 +202,10 @@ class SimpleDepthUpscaler:
                 if writer is not None:
                     for i in range(len(maps)):
                         writer.write(prev[i] if prev is not None else (out[i] >> 8).astype(np.uint8))
+                if writer16 is not None:
+                    full = out if out is not None else out_dev.cpu().numpy().view(np.uint16)
+                    for i in range(len(maps)):
+                        writer16.write(np.ascontiguousarray(full[i]))
             for f in pending:
                 f.result()
         finally:
@@ -206,13 +220,16 @@ class SimpleDepthUpscaler:
             pool.shutdown(wait=True)
             if writer is not None:
                 writer.release()
+            if writer16 is not None:
+                writer16.release()
         # what was produced is recorded next to the requested path; the 16-bit PNG sequence is the product, the mp4
         # only an 8-bit preview (and absent when preview=False or this OpenCV build has no encoder)
         import json
         have_video = out_path.exists() and out_path.stat().st_size > 0
         self._sidecar(out_path).write_text(json.dumps({"png16_dir": str(png_dir), "frames": len(depth_files),
                                                        "width": int(target_width), "height": int(target_height),
-                                                       "preview_video": str(out_path) if have_video else None}) + "\n")
+                                                       "preview_video": str(out_path) if have_video else None,
+                                                       "video16": str(path16) if writer16 is not None else None}) + "\n")
         print(f"✓ Depth frames saved: {png_dir}" + (f"  (8-bit preview: {output_path})" if have_video else ""))
         return output_path if have_video else str(png_dir)
 
