@@ -337,14 +337,16 @@ def test_two_lanes_from_two_host_threads():
 
 
 def test_fused_sweep_reports_clusters_and_matches_unfused_shapes():
-    """Shapes one cluster's shared memory can hold take the cluster-fused sweep (8 CTAs for D <= 128,
-    16 CTAs for D = 256); wider ones take the per-direction kernels.  Both must equal cv2."""
+    """Shapes one cluster's shared memory can hold take the cluster-fused sweep (9 or 8 CTAs for D <= 128,
+    16 CTAs for D = 256); wider ones take the per-direction kernels.  Both must equal cv2.  Includes widths where every
+    warp of the cluster gets a balanced share of 3+ columns (CPW or CPW - 1) and widths that fill warps in order."""
     for (W, H, D, expect_fused) in ((400, 40, 128, True), (600, 30, 256, True), (2100, 6, 256, True), (2300, 6, 256, False),
-                                    (2200, 6, 128, False)):
+                                    (2200, 6, 128, True), (2500, 6, 128, False), (1100, 9, 64, True), (1300, 7, 128, True),
+                                    (1000, 8, 128, True)):
         left, right, _ = synthetic.stereo_pair(8, 0, W, H, D)
         with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=1)) as ctx:
             d = ctx.sgbm_compute(torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda())[0].cpu().numpy()
-            assert (ctx.fused_sweep_clusters > 0) == expect_fused
+            assert (ctx.fused_sweep_clusters > 0) == expect_fused, (W, H, D, ctx.fused_sweep_clusters)
         assert np.array_equal(d, cv2_chain.make_matcher(D, 1).compute(left, right))
 
 

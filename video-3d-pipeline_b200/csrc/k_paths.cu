@@ -107,7 +107,7 @@ k_path_vert(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, 
 template <int NR, int CPW, int SMODE, int V3_CL, int V3_NW>
 __global__ void __launch_bounds__(V3_NW * 32, 1)
 k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, int H, int sy,
-             uint32_t P1p, uint32_t P2p)
+             uint32_t P1p, uint32_t P2p, int balanced)
 {
     using VT = typename Vec<NR>::T;
     extern __shared__ uint4 v3smem[];
@@ -119,7 +119,13 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     const int rank = (int)cluster.block_rank();
     const int frame = blockIdx.x / V3_CL;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int gcol0 = (rank * V3_NW + w) * CPW;       // first column this warp owns
+    // Columns per warp: `balanced` spreads the W1 columns over ALL warps of the cluster (CPW or CPW - 1 each, so every
+    // SM of the cluster carries the same share of the row); otherwise warps are filled with CPW columns in order and
+    // the last ones stay empty (narrow frames, where a balanced share would drop below the 3 columns the
+    // arrive / interior / wait schedule needs).
+    constexpr int NWT = V3_CL * V3_NW;
+    const int gw_ = rank * V3_NW + w;
+    const int gcol0 = balanced ? (int)((long long)gw_ * W1 / NWT) : gw_ * CPW;       // first column this warp owns
     const int lc0 = w * CPW;
     const VT* C = reinterpret_cast<const VT*>(Cv) + (size_t)frame * H * W1 * 32 + lane;
     VT* S = reinterpret_cast<VT*>(Sv) + (size_t)frame * H * W1 * 32 + lane;
@@ -137,8 +143,10 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     cluster.sync();
 
     constexpr int PARSTRIDE = V3_NW * 2 * 32;         // inbox elements per buffer
-    const int nv = min(max(W1 - gcol0, 0), CPW);      // columns of this warp inside the window
-    const bool has_right = gcol0 + CPW < W1;          // a column to the right of this warp's last one exists
+    const int nv = balanced ? (int)((long long)(gw_ + 1) * W1 / NWT) - gcol0
+                            : min(max(W1 - gcol0, 0), CPW);      // columns of this warp inside the window
+    const bool has_right = gcol0 + nv < W1;           // a column to the right of this warp's last one exists
+    V3D_DASSERT(nv >= 0 && nv <= CPW);
     VT cq[CPW];
     {
         const int y = sy > 0 ? 0 : H - 1;
@@ -222,17 +230,18 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         const uint32_t phase = (i >> 1) & 1;
         V3D_DASSERT(par == 0 || par == 1);                               // double-buffered inboxes: [par][warp][side]
         V3D_DASSERT((char*)(in_r + par * PARSTRIDE) + sizeof(VT) <= (char*)mb && y >= 0 && y < H);
-        if (has_right) st_async(to_r + par * PARSTRIDE * (uint32_t)sizeof(VT), Ml[(CPW - 1) * 32], to_r_bar + par * V3_NW * 8);
+        if (has_right) st_async(to_r + par * PARSTRIDE * (uint32_t)sizeof(VT), Ml[(nv - 1) * 32], to_r_bar + par * V3_NW * 8);
         if (has_left) st_async(to_l + par * PARSTRIDE * (uint32_t)sizeof(VT), Mr[0], to_l_bar + par * V3_NW * 8);
         if (lane == 0 && rx_bytes) mbar_expect_tx(my_bar + par * V3_NW, rx_bytes);
-        if (nv == CPW && CPW >= 3) {
-            // Full warp: the interior columns need nothing from other warps, so they run between the
-            // barrier's arrive and wait; only the two edge columns wait for the neighbours' states.
+        // A warp with NV >= 3 columns: the interior columns need nothing from other warps, so they run between the
+        // barrier's arrive and wait; only the two edge columns wait for the neighbours' states.
+        auto fast_row = [&](auto nvc) {
+            constexpr int NV = decltype(nvc)::value;
             uint32_t carry[NR], save_r1[NR], inr[NR];
             unpack<NR>(Ml[0], carry);                            // old state of column 0 -> column 1
             unpack<NR>(Mr[1 * 32], save_r1);                     // old state of column 1 -> column 0 (used last)
 #pragma unroll
-            for (int j = 1; j < CPW - 1; j++) {
+            for (int j = 1; j < NV - 1; j++) {
                 uint32_t nextcarry[NR];
                 unpack<NR>(Ml[j * 32], nextcarry);
                 unpack<NR>(Mr[(j + 1) * 32], inr);
@@ -253,7 +262,12 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
 #pragma unroll
                 for (int r = 0; r < NR; r++) edge[r] = 0;
             }
-            do_col(CPW - 1, carry, edge, more, Cnext, Snext, Srow);
+            do_col(NV - 1, carry, edge, more, Cnext, Snext, Srow);
+        };
+        if (nv == CPW && CPW >= 3) {
+            fast_row(std::integral_constant<int, CPW>{});
+        } else if (CPW >= 4 && nv == CPW - 1) {
+            fast_row(std::integral_constant<int, (CPW >= 4 ? CPW - 1 : 3)>{});
         } else {
             if (rx_bytes) mbar_wait(my_bar + par * V3_NW, phase);
             uint32_t carry[NR], inr[NR];
@@ -267,12 +281,8 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
                 if (j < nv) {
                     uint32_t nextcarry[NR];
                     unpack<NR>(Ml[j * 32], nextcarry);
-                    if (j + 1 < CPW) {
-                        unpack<NR>(Mr[(j + 1) * 32], inr);
-                        if (j + 1 >= nv) {
-#pragma unroll
-                            for (int r = 0; r < NR; r++) inr[r] = 0;
-                        }
+                    if (j + 1 < nv) {
+                        if (j + 1 < CPW) unpack<NR>(Mr[(j + 1) * 32], inr);
                     } else if (has_right) {
                         unpack<NR>(in_r[par * PARSTRIDE], inr);
                     } else {
@@ -290,8 +300,9 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     cluster.sync();   // nobody may exit while a neighbour can still read its shared memory
 }
 
+// Launch (or, with query != nullptr, only ask how many clusters are co-resident) one fused sweep configuration.
 template <int NR, int CPW, int V3_CL, int V3_NW>
-int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
+int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st, int* query)
 {
     using VT = typename Vec<NR>::T;
     const size_t smem = ((size_t)3 * V3_NW * CPW * 32 + (size_t)2 * V3_NW * 2 * 32) * sizeof(VT) + (size_t)2 * V3_NW * 8;
@@ -312,25 +323,42 @@ int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = V3_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (query) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kw, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        *query = n;
+        return V3D_OK;
+    }
     const uint16_t* C = ctx->C;
     uint16_t* S = ctx->S;
     const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
-    if (!ctx->max_clusters) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, kw, &cfg) == cudaSuccess) ctx->max_clusters = n;
-        else cudaGetLastError();
-        if (ctx->max_clusters <= 0) {      // this device cannot co-schedule an 8-CTA cluster of this size:
-            ctx->max_clusters = 0;         // use the one-direction-per-launch kernels from now on
-            ctx->no_fused_vertical = 1;
-            return V3D_ESTATE;
-        }
-    }
-    V3D_CUDA(cudaLaunchKernelEx(&cfg, accum ? ka : kw, C, S, ctx->W1, ctx->H, sy, P1p, P2p));
+    // every warp of the cluster gets CPW or CPW - 1 columns when that leaves each at least 3 (see the kernel)
+    const int balanced = ctx->W1 / (V3_CL * V3_NW) >= 3 ? 1 : 0;
+    V3D_CUDA(cudaLaunchKernelEx(&cfg, accum ? ka : kw, C, S, ctx->W1, ctx->H, sy, P1p, P2p, balanced));
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
 
+// Columns per warp the frame needs with CL x NW warps per cluster -> the instantiation that holds them.
+// Returns 1 when the configuration ran (or was queried), 0 when the frame is wider than the cluster's shared memory.
+template <int NR, int CL, int NW>
+int vert3_dispatch(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st, int* query, int& rc)
+{
+    const int need = (ctx->W1 + CL * NW - 1) / (CL * NW);
+    if (need <= 2) rc = launch_vert3<NR, 2, CL, NW>(ctx, batch, sy, accum, st, query);
+    else if (need <= 4) rc = launch_vert3<NR, 4, CL, NW>(ctx, batch, sy, accum, st, query);
+    else if (need <= 5) rc = launch_vert3<NR, 5, CL, NW>(ctx, batch, sy, accum, st, query);
+    else if (need <= 6) rc = launch_vert3<NR, 6, CL, NW>(ctx, batch, sy, accum, st, query);
+    else if (need <= 7) rc = launch_vert3<NR, 7, CL, NW>(ctx, batch, sy, accum, st, query);
+    else if (need <= 8 && NR <= 2) rc = launch_vert3<NR, (NR <= 2 ? 8 : 7), CL, NW>(ctx, batch, sy, accum, st, query);
+    else return 0;      // wider than one cluster's shared memory: per-direction kernels
+    return 1;
+}
+
 // Returns 1 when the fused sweep ran, 0 when the shape does not fit it (caller falls back), < 0 on error.
+// Cluster size: 16 CTAs for D = 256 (512-byte state vectors); for D <= 128 whichever of 9 and 8 CTAs keeps more SMs
+// busy on THIS device -- clusters live inside a GPC, and on B200 15 clusters are co-resident at either size, so 9 CTAs
+// per frame use 135 SMs where 8 use 120 (tools/probe_clusters.cu lists every size).
 template <int NR>
 int try_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
 {
@@ -341,18 +369,30 @@ int try_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
 #ifndef V3D_V3_NW2
 #define V3D_V3_NW2 32
 #endif
-    constexpr int CL = NR <= 2 ? 8 : 16, NW = NR <= 2 ? V3D_V3_NW2 : V3D_V3_NW4;
-    const int need = (ctx->W1 + CL * NW - 1) / (CL * NW);
-    int rc;
-    if (need <= 2) rc = launch_vert3<NR, 2, CL, NW>(ctx, batch, sy, accum, st);
-    else if (need <= 4) rc = launch_vert3<NR, 4, CL, NW>(ctx, batch, sy, accum, st);
-    else if (need <= 5 && NR > 2) rc = launch_vert3<NR, (NR > 2 ? 5 : 7), CL, NW>(ctx, batch, sy, accum, st);
-    else if (need <= 6 && NR > 2) rc = launch_vert3<NR, (NR > 2 ? 6 : 7), CL, NW>(ctx, batch, sy, accum, st);
-    else if (need <= 7) rc = launch_vert3<NR, 7, CL, NW>(ctx, batch, sy, accum, st);
-    else if (need <= 8 && NR <= 2) rc = launch_vert3<NR, (NR <= 2 ? 8 : 7), CL, NW>(ctx, batch, sy, accum, st);
-    else return 0;      // wider than one cluster's shared memory: per-direction kernels
-    if (rc == V3D_ESTATE && ctx->no_fused_vertical) return 0;     // not schedulable here: caller falls back
-    return rc ? rc : 1;
+#ifndef V3D_V3_CL2
+#define V3D_V3_CL2 9
+#endif
+    constexpr int NW = NR <= 2 ? V3D_V3_NW2 : V3D_V3_NW4;
+    constexpr int CLA = NR <= 2 ? V3D_V3_CL2 : 16, CLB = NR <= 2 ? 8 : 16;     // preferred / portable cluster size
+    int rc = V3D_OK;
+    if (!ctx->v3_cl) {
+        int na = 0, nb = 0;
+        const int fa = vert3_dispatch<NR, CLA, NW>(ctx, batch, sy, accum, st, &na, rc);
+        if (rc) return rc;
+        const int fb = CLB != CLA ? vert3_dispatch<NR, CLB, NW>(ctx, batch, sy, accum, st, &nb, rc) : 0;
+        if (rc) return rc;
+        if (fa && na > 0 && (!fb || na * CLA >= nb * CLB)) { ctx->v3_cl = CLA; ctx->max_clusters = na; }
+        else if (fb && nb > 0) { ctx->v3_cl = CLB; ctx->max_clusters = nb; }
+        else {                             // too wide, or this device cannot co-schedule such a cluster:
+            ctx->max_clusters = 0;         // use the one-direction-per-launch kernels from now on
+            ctx->no_fused_vertical = 1;
+            return 0;
+        }
+    }
+    const int fit = ctx->v3_cl == CLA ? vert3_dispatch<NR, CLA, NW>(ctx, batch, sy, accum, st, nullptr, rc)
+                                      : vert3_dispatch<NR, CLB, NW>(ctx, batch, sy, accum, st, nullptr, rc);
+    if (rc) return rc;
+    return fit;
 }
 
 template <int NR>

@@ -69,6 +69,7 @@ struct v3d_ctx {
     int guided_attr_set;
     int fixed_scale; float scale_lo, scale_hi;     // v3d_set_depth_scale (0 = per-frame min-max, the reference)
     int max_clusters;        // co-resident frame clusters of the fused vertical sweep (0 = not queried)
+    int v3_cl;               // CTAs per cluster the fused sweep runs with on this device (0 = not chosen yet)
     int no_fused_vertical;
     int h_attr_set;
     unsigned long long cost_attr_set;   // test hook: force the one-direction-per-launch path kernels
