@@ -21,6 +21,9 @@
 namespace {
 
 constexpr int GRMAX = 8;    // largest supported radius
+#ifndef V3D_GUIDED_DEPTH_PREFETCH
+#define V3D_GUIDED_DEPTH_PREFETCH 0
+#endif
 
 __device__ __forceinline__ int reflect_idx(int i, int n)
 {
@@ -229,6 +232,16 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
         if (tid < R) taps[(g + 1) & 1][tid] = make_tap((g + 1) * R + tid);
         __syncthreads();
         stage_rows(g + 1);                                           // lands while the horizontal pass runs
+#if V3D_GUIDED_DEPTH_PREFETCH
+        if ((g + 1) * R < nrows) {                                   // the next group's depth taps: into L1 behind the horizontal pass
+            const RowTap* tn = taps[(g + 1) & 1];
+#pragma unroll
+            for (int jj = 0; jj < R; jj++) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(dx0 + tn[jj].o0));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(dx0 + tn[jj].o1));
+            }
+        }
+#endif
 
         // horizontal pass + 3x3 solve
         const float kn = k255 * inv_n, kkn = k255 * k255 * inv_n;
@@ -461,6 +474,13 @@ k_guided_apply_s(const float4* __restrict__ ab, const uint8_t* __restrict__ guid
             const int Y = Y0 + o;
             const float4* vr = vbuf + jj * VP + xb + run;          // window start; xb is a multiple of GR
             auto at = [&](int dx) -> float4 { return vr[RT > 0 ? dx + dx / GR : (xb + dx) + (xb + dx) / GR - xb - run]; };
+            const size_t base = (size_t)Y * gw + X;
+            // the run's 24 guide bytes are requested before the window sums so that their latency hides behind them
+            uint2 u0 = make_uint2(0u, 0u), u1 = u0, u2 = u0;
+            if (VEC) {
+                const uint2* gp = reinterpret_cast<const uint2*>(guide + base * 3);
+                u0 = __ldg(gp); u1 = __ldg(gp + 1); u2 = __ldg(gp + 2);
+            }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (RT > 0) {
 #pragma unroll
@@ -469,11 +489,8 @@ k_guided_apply_s(const float4* __restrict__ ab, const uint8_t* __restrict__ guid
 #pragma unroll 1
                 for (int t = 0; t <= 2 * r; t++) add4(acc, at(t));
             }
-            const size_t base = (size_t)Y * gw + X;
             if (VEC) {
                 static_assert(!VEC || GR == 8, "vector path writes runs of 8");
-                const uint2* gp = reinterpret_cast<const uint2*>(guide + base * 3);
-                const uint2 u0 = __ldg(gp), u1 = __ldg(gp + 1), u2 = __ldg(gp + 2);
                 const uint32_t gb[6] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y};
                 uint32_t packed[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
