@@ -19,6 +19,9 @@ namespace {
 #ifndef V3D_COST_HN
 #define V3D_COST_HN 4
 #endif
+#ifndef V3D_COST_HOIST_WAITS
+#define V3D_COST_HOIST_WAITS 1
+#endif
 constexpr int TXW = 32;       // window columns per block (one warp each); TXW - 2R of them are output columns
 constexpr int PADL = 32;      // front padding (elements) of the reversed right-image rows
 
@@ -268,11 +271,16 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     // horizontal pass, and this warp's arrival on the group's barrier.  pgc is a compile-time constant.
     auto cost_rows = [&](auto pgc, uint32_t par) {
         constexpr int pg = decltype(pgc)::value;
+#if V3D_COST_HOIST_WAITS
+#pragma unroll
+        for (int s = 0; s < RPB; s++) mbar_wait_a(bar0 + (pg + s) * 8, par);    // both rows' copies first: the loads of the second row may then overlap the arithmetic of the first
+#endif
 #pragma unroll
         for (int s = 0; s < RPB; s++) {
-            constexpr int dummy = 0; (void)dummy;
             const int ph = pg + s;
+#if !V3D_COST_HOIST_WAITS
             mbar_wait_a(bar0 + ph * 8, par);
+#endif
             const uint4 ls = l_p[ph * LSTG + 0];
             const uint4 li = l_p[ph * LSTG + 1];
 #pragma unroll

@@ -248,21 +248,27 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
             key = min(key, __shfl_xor_sync(V3D_FULL_MASK, key, 1));
             key = min(key, __shfl_xor_sync(V3D_FULL_MASK, key, 2));
             const uint32_t best = key & 0xffu, minS = key >> 8;
-            // uniqueness: the smallest S over |d - best| > 1
-            const uint32_t off = ((1u - best) & 0xffffu) * 0x10001u;      // t = d - best + 1 in each half
+            // uniqueness: the smallest S over |d - best| > 1.  One lane per pixel takes the sub-pixel neighbours and
+            // then blanks S[best-1 .. best+1] in the staged chunk, so that the second minimum is a plain packed minimum
+            // over the re-read row (1 instruction per two disparities instead of 5 for a masked one).
+            uint16_t* s16 = reinterpret_cast<uint16_t*>(sst + st * CH * STEP_B + wp * STEP_B);
+            uint32_t sm1 = 0, sp1 = 0;
+            if (wq == 0) {
+                sm1 = s16[best > 0 ? best - 1 : 0];
+                sp1 = s16[best < D - 1 ? best + 1 : D - 1];
+                s16[best] = 0xffffu;
+                if (best > 0) s16[best - 1] = 0xffffu;
+                if (best < D - 1) s16[best + 1] = 0xffffu;
+            }
+            __syncwarp();
             uint32_t m2 = 0xffffffffu;
 #pragma unroll
             for (int k = 0; k < NU; k++) {
                 const int u = NR == 2 ? ((k + rot) & 3) : k;
-                const uint32_t d0 = (uint32_t)(wq * NU + u) * 8;
-                const uint32_t idx0 = d0 | ((d0 + 1) << 16);
-                const uint32_t w[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const uint32_t tt = __vadd2(idx0 + t * 0x00020002u, off);
-                    const uint32_t e = __vadd2(__vminu2(tt, 0x00030003u), 0xfffdfffdu);   // 0xfffd.. iff tt in {0,1,2}
-                    m2 = __vminu2(m2, __vmaxu2(w[t], e));
-                }
+                uint4 w4 = px[u];
+                if (PAD && (int)((wq * NU + u) * 8) >= Dreal) w4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                m2 = __vimin3_u16x2(m2, w4.x, w4.y);
+                m2 = __vimin3_u16x2(m2, w4.z, w4.w);
             }
             m2 = __vminu2(m2, __byte_perm(m2, 0, 0x1032));
             m2 = __vminu2(m2, __shfl_xor_sync(V3D_FULL_MASK, m2, 1));
@@ -270,9 +276,6 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
             const uint32_t minS2 = m2 & 0xffffu;
             if (wq == 0 && wp < n) {
                 const bool reject = minS2 * (uint32_t)(100 - uniq) < minS * 100u;
-                const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sst + st * CH * STEP_B + wp * STEP_B);
-                const uint32_t sm1 = s16[best > 0 ? best - 1 : 0];
-                const uint32_t sp1 = s16[best < D - 1 ? best + 1 : D - 1];
                 rec[lo + wp] = make_uint2((minS & 0xffffu) | ((reject ? 0xffffu : best) << 16), sm1 | (sp1 << 16));
             }
         }
