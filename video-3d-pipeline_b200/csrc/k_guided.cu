@@ -75,7 +75,7 @@ __host__ __device__ constexpr int row_pitch()
 // The coefficient kernel's horizontal pass splits every run of 8 outputs over a lane pair when it can (radius 8,
 // one row of the group per warp).
 template <int RT, int NT, int R, int GR>
-__host__ __device__ constexpr bool paired_pass() { return RT == 8 && GR == 8 && NT == 32 * R; }
+__host__ __device__ constexpr bool paired_pass() { return RT == 8 && GR == 8 && NT % (32 * R) == 0; }
 
 // shared-memory bytes of k_guided_coeff_s
 template <int RT, int NT, int R, int GR>
@@ -283,10 +283,13 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
             // (17 columns, 4 apart) overlap in 13 columns: each lane sums half of the overlap plus its own 4 columns, the
             // halves are exchanged with one shuffle per plane, then each lane slides its window over its 4 outputs.
             // 28 of 32 lanes work, against 56 of 128 threads when one thread owns a whole run.
-            const int lane = tid & 31, jj = tid >> 5;
+            constexpr int WPR = NT / (32 * R);                      // warps per row of the group (1 at 128 threads)
+            const int lane = tid & 31, jj = (tid >> 5) / WPR;
+            const int rpw = (runs + WPR - 1) / WPR;                 // runs per warp (<= 16: one per lane of a half-warp)
             const int o = g * R + jj - 2 * RT;                      // output row of this warp in this group (warp-uniform)
             if (o >= 0 && o < seg_h) {
-                const int half = lane >> 4, run_raw = lane & 15;
+                const int half = lane >> 4;
+                const int run_raw = (lane & 15) < rpw ? ((tid >> 5) % WPR) * rpw + (lane & 15) : runs;
                 const int run = min(run_raw, runs - 1), xb = run * GR;      // lanes past the last run repeat it, store nothing
                 const float4* vr = vbuf + jj * VP + xb + run;           // slot of the run's first column
                 const float* vs = v12 + jj * VP + xb + run;

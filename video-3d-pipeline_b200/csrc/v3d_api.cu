@@ -165,7 +165,13 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     // side stream of the path chain (k_paths.cu); V3D_NO_SIDE_STREAM=1 keeps the chain on one stream
     const char* ns = getenv("V3D_NO_SIDE_STREAM");
     if (!(ns && ns[0] == '1')) {
-        if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        // highest priority: the pass it carries is HBM-bound, so its blocks should take the next free block slot on any SM
+        // (next to other lanes' integer-bound kernels) instead of queueing behind them; V3D_SIDE_PRIORITY=0 = default priority
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const char* sp = getenv("V3D_SIDE_PRIORITY");
+        const int prio = (sp && sp[0] == '0') ? prio_lo : prio_hi;
+        if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
