@@ -77,6 +77,24 @@ def test_random_guided_upscale_shapes(seed):
     assert np.abs(out.astype(np.int64) - ou.astype(np.int64)).max() <= 1
 
 
+@pytest.mark.parametrize("r,w,h,gw,gh", [(9, 90, 60, 200, 131), (12, 120, 70, 240, 140), (16, 100, 80, 233, 177), (16, 40, 30, 33, 33)])
+def test_guided_upscale_large_radii(r, w, h, gw, gh):
+    """Radii beyond the reference value (8): the run-time-radius instantiation up to r = 16, same tolerance."""
+    from oracle import guided as og
+    depth = synthetic.depth_u16(r, 0, w, h)
+    guide = synthetic.guide_frame(r, 0, gw, gh)
+    with nv.Context(80, 8, nv.SgbmParams()) as ctx:
+        out, q = ctx.guided_upscale(torch.from_numpy(depth.view(np.int16))[None].cuda().view(torch.uint16),
+                                    torch.from_numpy(guide)[None].cuda(), r, 1e-3, want_q=True)
+        out, q = out[0].cpu().numpy().view(np.uint16), q[0].cpu().numpy()
+        with pytest.raises(ValueError):
+            ctx.guided_upscale(torch.from_numpy(depth.view(np.int16))[None].cuda().view(torch.uint16),
+                               torch.from_numpy(guide)[None].cuda(), 17, 1e-3)
+    oq, ou = og.guided_upscale(depth, guide, r, 1e-3)
+    assert float(np.abs(q - oq).max()) * 65535 < 0.5
+    assert np.abs(out.astype(np.int64) - ou.astype(np.int64)).max() <= 1
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_random_split_gray_unsqueeze(seed):
     from oracle import sgbm as osg

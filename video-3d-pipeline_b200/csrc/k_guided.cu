@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int GRMAX = 8;    // largest supported radius
+constexpr int GRMAX = 16;   // largest supported radius (8 and 4 have compile-time instantiations, the rest take the run-time one)
 #ifndef V3D_GUIDED_DEPTH_PREFETCH
 #define V3D_GUIDED_DEPTH_PREFETCH 0
 #endif
