@@ -1,7 +1,8 @@
-# A/B of kernel variants on one box: tools/ab.sh <lib.so|default> ...   (bench stage times, one lane-serial + default lanes)
+# A/B of kernel variants on one box: tools/ab.sh [--config cfgN] <lib.so|default> ...   (bench stage times)
+CFG=cfg4; if [ "$1" = "--config" ]; then CFG=$2; shift 2; fi
 for v in "$@"; do
   if [ "$v" = default ]; then unset V3D_LIB; else export V3D_LIB=$PWD/$v; fi
-  timeout 300 python bench.py --steps 5 --warmup 2 --reps 1 --no-cpu-baseline --no-depth-only > gpurun_out/ab_$(basename $v .so).json 2> gpurun_out/ab_$(basename $v .so).err
+  timeout 300 python bench.py --config $CFG --steps 5 --warmup 2 --reps 1 --no-cpu-baseline --no-depth-only > gpurun_out/ab_$(basename $v .so).json 2> gpurun_out/ab_$(basename $v .so).err
   python - <<PY
 import json
 try:

@@ -125,7 +125,8 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     // arrive / interior / wait schedule needs).
     constexpr int NWT = V3_CL * V3_NW;
     const int gw_ = rank * V3_NW + w;
-    const int gcol0 = balanced ? (int)((long long)gw_ * W1 / NWT) : gw_ * CPW;       // first column this warp owns
+    constexpr bool CAN_BALANCE = NR <= 2;           // (D = 256 never balances: see launch_vert3)
+    const int gcol0 = (CAN_BALANCE && balanced) ? (int)((long long)gw_ * W1 / NWT) : gw_ * CPW;       // first column this warp owns
     const int lc0 = w * CPW;
     const VT* C = reinterpret_cast<const VT*>(Cv) + (size_t)frame * H * W1 * 32 + lane;
     VT* S = reinterpret_cast<VT*>(Sv) + (size_t)frame * H * W1 * 32 + lane;
@@ -143,9 +144,9 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     cluster.sync();
 
     constexpr int PARSTRIDE = V3_NW * 2 * 32;         // inbox elements per buffer
-    const int nv = balanced ? (int)((long long)(gw_ + 1) * W1 / NWT) - gcol0
-                            : min(max(W1 - gcol0, 0), CPW);      // columns of this warp inside the window
-    const bool has_right = gcol0 + nv < W1;           // a column to the right of this warp's last one exists
+    const int nv = (CAN_BALANCE && balanced) ? (int)((long long)(gw_ + 1) * W1 / NWT) - gcol0
+                                             : min(max(W1 - gcol0, 0), CPW);      // columns of this warp inside the window
+    const bool has_right = CAN_BALANCE ? gcol0 + nv < W1 : gcol0 + CPW < W1;   // a column to the right of this warp's last one exists
     V3D_DASSERT(nv >= 0 && nv <= CPW);
     VT cq[CPW];
     {
@@ -230,7 +231,8 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         const uint32_t phase = (i >> 1) & 1;
         V3D_DASSERT(par == 0 || par == 1);                               // double-buffered inboxes: [par][warp][side]
         V3D_DASSERT((char*)(in_r + par * PARSTRIDE) + sizeof(VT) <= (char*)mb && y >= 0 && y < H);
-        if (has_right) st_async(to_r + par * PARSTRIDE * (uint32_t)sizeof(VT), Ml[(nv - 1) * 32], to_r_bar + par * V3_NW * 8);
+        // (a warp with a right neighbour is full unless the columns are balanced; a compile-time index where possible)
+        if (has_right) st_async(to_r + par * PARSTRIDE * (uint32_t)sizeof(VT), Ml[((NR <= 2 && CPW >= 4 ? nv : CPW) - 1) * 32], to_r_bar + par * V3_NW * 8);
         if (has_left) st_async(to_l + par * PARSTRIDE * (uint32_t)sizeof(VT), Mr[0], to_l_bar + par * V3_NW * 8);
         if (lane == 0 && rx_bytes) mbar_expect_tx(my_bar + par * V3_NW, rx_bytes);
         // A warp with NV >= 3 columns: the interior columns need nothing from other warps, so they run between the
@@ -264,10 +266,44 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
             }
             do_col(NV - 1, carry, edge, more, Cnext, Snext, Srow);
         };
+        // (the second instantiation of the row body only where the balanced distribution uses it: at D = 256 it costs
+        // registers -- spills -- and instruction cache for nothing)
+        constexpr bool TWO_WIDTHS = NR <= 2 && CPW >= 4;
         if (nv == CPW && CPW >= 3) {
-            fast_row(std::integral_constant<int, CPW>{});
-        } else if (CPW >= 4 && nv == CPW - 1) {
-            fast_row(std::integral_constant<int, (CPW >= 4 ? CPW - 1 : 3)>{});
+            if constexpr (TWO_WIDTHS) {
+                fast_row(std::integral_constant<int, CPW>{});
+            } else {
+                // written out (not through the generic lambda): the D = 256 sweep is register-starved (96 registers, 18
+                // warps) and loses 15 % when the body goes through the lambda
+                uint32_t carry[NR], save_r1[NR], inr[NR];
+                unpack<NR>(Ml[0], carry);
+                unpack<NR>(Mr[1 * 32], save_r1);
+#pragma unroll
+                for (int j = 1; j < CPW - 1; j++) {
+                    uint32_t nextcarry[NR];
+                    unpack<NR>(Ml[j * 32], nextcarry);
+                    unpack<NR>(Mr[(j + 1) * 32], inr);
+                    do_col(j, carry, inr, more, Cnext, Snext, Srow);
+#pragma unroll
+                    for (int r = 0; r < NR; r++) carry[r] = nextcarry[r];
+                }
+                if (rx_bytes) mbar_wait(my_bar + par * V3_NW, phase);
+                uint32_t edge[NR];
+                if (gcol0 > 0) unpack<NR>(in_l[par * PARSTRIDE], edge);
+                else {
+#pragma unroll
+                    for (int r = 0; r < NR; r++) edge[r] = 0;
+                }
+                do_col(0, edge, save_r1, more, Cnext, Snext, Srow);
+                if (has_right) unpack<NR>(in_r[par * PARSTRIDE], edge);
+                else {
+#pragma unroll
+                    for (int r = 0; r < NR; r++) edge[r] = 0;
+                }
+                do_col(CPW - 1, carry, edge, more, Cnext, Snext, Srow);
+            }
+        } else if (TWO_WIDTHS && nv == CPW - 1) {
+            if constexpr (TWO_WIDTHS) fast_row(std::integral_constant<int, CPW - 1>{});
         } else {
             if (rx_bytes) mbar_wait(my_bar + par * V3_NW, phase);
             uint32_t carry[NR], inr[NR];
@@ -333,7 +369,9 @@ int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st, i
     uint16_t* S = ctx->S;
     const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
     // every warp of the cluster gets CPW or CPW - 1 columns when that leaves each at least 3 (see the kernel)
-    const int balanced = ctx->W1 / (V3_CL * V3_NW) >= 3 ? 1 : 0;
+    // (not for D = 256: two instantiations of the row body per kernel thrash the instruction cache there -- measured 8.05
+    // vs 7.25 ms for the two sweeps of cfg5)
+    const int balanced = NR <= 2 && ctx->W1 / (V3_CL * V3_NW) >= 3 ? 1 : 0;
     V3D_CUDA(cudaLaunchKernelEx(&cfg, accum ? ka : kw, C, S, ctx->W1, ctx->H, sy, P1p, P2p, balanced));
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;

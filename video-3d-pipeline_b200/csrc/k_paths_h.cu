@@ -17,6 +17,7 @@ constexpr int CH = 8;         // pixel steps per staged chunk
 #ifndef V3D_WTA_NST
 #define V3D_WTA_NST 2       // staged chunks per warp of the last path kernel (2: three blocks per SM; 3 measured 3 % slower)
 #endif
+__host__ __device__ constexpr int wta_stages(int nr) { return nr == 4 ? 3 : V3D_WTA_NST; }   // D = 256: one block per SM either way, deeper staging wins
 
 // ------------------------------------------------------------------------------------------
 // left -> right (predecessor x-1), CHECKPOINT pass.  The left-to-right costs L are never written: this kernel
@@ -124,7 +125,7 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
 {
     using VT = typename Vec<NR>::T;
     constexpr int D = 64 * NR;
-    constexpr int NST = V3D_WTA_NST;
+    constexpr int NST = wta_stages(NR);
     constexpr int STEP_B = 128 * NR;
     constexpr int NU = 2 * NR;                   // uint4 (8 disparities each) per lane in the WTA phase
     static_assert(CH == 8, "the WTA lane mapping assumes 8 pixels per chunk");
@@ -147,7 +148,7 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
     const int wp = lane >> 2, wq = lane & 3;
     // visit the NU uint4 in a lane-dependent rotation so that a quarter-warp's 128-bit loads hit 8 different
     // 16-byte bank groups (the natural order is a 4-way conflict for D = 128)
-    const int rot = NR == 2 ? (((wq >> 1) + 2 * (wp & 1)) & 3) : 0;
+    const int rot = NR == 2 ? (((wq >> 1) + 2 * (wp & 1)) & 3) : NR == 4 ? ((wq + 4 * (wp & 1)) & 7) : (wp & 1);   // D = 256: the natural order is an 8-way conflict
 
     if (lane == 0) {
 #pragma unroll
@@ -232,7 +233,7 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
             uint32_t key = 0xffffffffu;
 #pragma unroll
             for (int k = 0; k < NU; k++) {
-                const int u = NR == 2 ? ((k + rot) & 3) : k;
+                const int u = (k + rot) & (NU - 1);
                 v[k] = px[u];
                 const uint32_t d0 = (uint32_t)(wq * NU + u) * 8;
                 if (TAP_S && wp < n) Stap[(size_t)(lo + wp) * (STEP_B / 16) + wq * NU + u] = v[k];
@@ -264,7 +265,7 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
             uint32_t m2 = 0xffffffffu;
 #pragma unroll
             for (int k = 0; k < NU; k++) {
-                const int u = NR == 2 ? ((k + rot) & 3) : k;
+                const int u = (k + rot) & (NU - 1);
                 uint4 w4 = px[u];
                 if (PAD && (int)((wq * NU + u) * 8) >= Dreal) w4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
                 m2 = __vimin3_u16x2(m2, w4.x, w4.y);
@@ -303,7 +304,7 @@ int launch_wta(v3d_ctx* ctx, int batch, cudaStream_t st, bool tap_s)
 {
     const int rows = batch * ctx->H;
     const uint32_t P1p = (uint32_t)ctx->P1 * 0x10001u, P2p = (uint32_t)ctx->P2 * 0x10001u;
-    const size_t smem = (size_t)HW_WARPS * (2 * CH + 1) * V3D_WTA_NST * 128 * NR;
+    const size_t smem = (size_t)HW_WARPS * (2 * CH + 1) * wta_stages(NR) * 128 * NR;
     dim3 grid((rows + HW_WARPS - 1) / HW_WARPS), block(HW_WARPS * 32);
     const bool pad = ctx->D != ctx->Dk;
     auto wta = tap_s ? (pad ? k_path_rl_wta_tma<NR, true, true> : k_path_rl_wta_tma<NR, true, false>)
