@@ -40,14 +40,14 @@ extern "C" {
 #define V3D_ECUDA    (-3)  /* CUDA runtime error or no device */
 #define V3D_ESTATE   (-4)  /* call sequence error (e.g. tap before compute) */
 
-#define V3D_INVALID_DISP (-16)   /* cv2: (minDisparity - 1) * 16 */
+#define V3D_INVALID_DISP (-16)   /* cv2: (minDisparity - 1) * 16; this is the value for minDisparity = 0 */
 
 #define V3D_MODE_SGBM 0          /* 5 path directions (cv2.STEREO_SGBM_MODE_SGBM) */
 #define V3D_MODE_HH   1          /* 8 path directions (cv2.STEREO_SGBM_MODE_HH)   */
 
 /* cv2.StereoSGBM_create arguments, depth.py:315-325.  Field order is ABI. */
 typedef struct v3d_sgbm_params {
-    int32_t minDisparity;      /* must be 0 (depth.py:316) */
+    int32_t minDisparity;      /* 0 in the reference (depth.py:316); -1024 .. 1024 accepted, cv2 semantics */
     int32_t numDisparities;    /* positive multiple of 16, <= 256 (cv2's rule); kernels run at 64/128/256 */
     int32_t blockSize;         /* 5 (depth.py:318); 1,3,5,7 accepted */
     int32_t P1, P2;            /* depth.py:319-320 */
@@ -114,7 +114,8 @@ int v3d_sgbm_compute(v3d_ctx* ctx, const uint8_t* left_gray, const uint8_t* righ
 int v3d_set_debug_taps(v3d_ctx* ctx, int enabled);
 
 /* Parity-test taps into the workspace of the LAST v3d_sgbm_compute call.
- * which: 0 = block cost C  [batch][H][W1][Dk] uint16, Dk = numDisparities rounded up to 64/128/256
+ * which: 0 = block cost C  [batch][H][W1][Dk] uint16, Dk = numDisparities rounded up to 64/128/256,
+ *            W1 = (W + min(minDisparity, 0)) - max(minDisparity + numDisparities, 0)
  *        1 = aggregated S  [batch][H][W1][Dk] uint16 (unsaturated sum); d >= numDisparities is padding
  *        2 = raw disparity (pre-median)  [batch][H][W] int16
  *        3 = post-median, pre-speckle    [batch][H][W] int16

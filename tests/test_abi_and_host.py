@@ -50,7 +50,8 @@ def test_create_validates_before_touching_cuda():
         (_native.SgbmParams(numDisparities=64), 66, 20),        # W - D <= blockSize/2 : cv2.error site
         (_native.SgbmParams(numDisparities=40), 400, 20),       # not a multiple of 16 (cv2 rejects it too)
         (_native.SgbmParams(numDisparities=272), 600, 20),      # beyond the largest kernel instantiation
-        (_native.SgbmParams(minDisparity=1), 400, 20),
+        (_native.SgbmParams(minDisparity=2000), 4000, 20),      # (minDisparity + numDisparities) * 16 must fit int16
+        (_native.SgbmParams(minDisparity=20), 86, 20),          # window [84, 86) not wider than blockSize/2: cv2.error site
         (_native.SgbmParams(blockSize=4), 400, 20),
         (_native.SgbmParams(mode=2), 400, 20),
         (_native.SgbmParams(P2=60000), 400, 20),                # packed 16-bit state would overflow

@@ -51,6 +51,32 @@ def test_random_shapes_and_parameters_match_cv2(seed):
     assert np.array_equal(got, ref), dict(D=D, mode=mode, W=W, H=H, kind=kind, **kw)
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_random_min_disparity_matches_cv2(seed):
+    """The same sweep with a random minDisparity in [-48, 64] (cv2: window [max(minD + D, 0), W + min(minD, 0)),
+    invalid value (minD - 1) * 16)."""
+    D, mode, W, H, kw, kind, rng = _case(200 + seed)
+    minD = int(rng.integers(-48, 65))
+    W += abs(minD)                                       # keep the window wider than the block radius
+    left, right, _ = synthetic.stereo_pair(seed, 0, W, H, D)
+    if kind % 2:
+        right = np.roll(right, minD, axis=1)
+    try:
+        ref = cv2_chain.make_matcher(D, mode, minDisparity=minD, **kw).compute(left, right)
+    except Exception as e:                               # cv2.error for degenerate windows
+        with pytest.raises(ValueError):
+            nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=mode, minDisparity=minD, **kw))
+        return
+    try:
+        ctx = nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=mode, minDisparity=minD, **kw))
+    except ValueError as e:
+        assert "too large" in str(e)
+        pytest.skip(str(e))
+    with ctx:
+        got = ctx.sgbm_compute(torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda())[0].cpu().numpy()
+    assert np.array_equal(got, ref), dict(D=D, mode=mode, W=W, H=H, minD=minD, **kw)
+
+
 @pytest.mark.parametrize("seed", list(range(12)) + [56, 57, 70, 83])
 def test_random_guided_upscale_shapes(seed):
     """Arbitrary (non-integer) scale factors, radii and eps (1e-4 .. 1e-2): the fp32 kernels stay within the

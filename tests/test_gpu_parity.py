@@ -445,3 +445,25 @@ def test_row_checkpoints_cover_every_width_remainder():
         _run_stages(W1 + 64, 12, 64, 0)
     _run_stages(128 + 21, 9, 128, 1)
     _run_stages(256 + 13, 6, 256, 0)
+
+
+@pytest.mark.parametrize("minD,W,H,D,mode", [(16, 300, 40, 64, 0), (5, 260, 30, 64, 1), (48, 420, 24, 128, 0), (-16, 300, 40, 64, 0),
+                                             (-5, 231, 17, 48, 1), (-70, 300, 20, 64, 0), (-64, 280, 16, 64, 0), (100, 700, 12, 256, 0),
+                                             (1, 150, 9, 16, 0)])
+def test_min_disparity_matches_cv2(minD, W, H, D, mode):
+    """minDisparity != 0 (outside the reference's literals, inside cv2's contract): window [max(minD + D, 0),
+    W + min(minD, 0)), invalid value (minD - 1) * 16, disparities offset by minD -- final map bit-exact vs cv2, with and
+    without the speckle filter."""
+    left, right, _ = synthetic.stereo_pair(21, 0, W, H, D)
+    right = np.roll(right, minD // 2, axis=1)                 # some matches inside the shifted range
+    for kw in (dict(), dict(speckleWindowSize=0, uniquenessRatio=0)):
+        with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=mode, minDisparity=minD, **kw)) as ctx:
+            lt, rt = torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda()
+            d = ctx.sgbm_compute(lt, rt)[0].cpu().numpy()
+            f32, u16 = ctx.postprocess(torch.from_numpy(d)[None].cuda())
+        ref = cv2_chain.make_matcher(D, mode, minDisparity=minD, **kw).compute(left, right)
+        assert np.array_equal(d, ref), (minD, kw, float((d != ref).mean()))
+        depth = ref.astype(np.float32) / 16.0                  # depth.py:341, 374, 400-403 on that map
+        depth[depth <= 0] = 0
+        assert np.array_equal(f32[0].cpu().numpy(), depth)
+        assert np.array_equal(_u16(u16)[0], cv2_chain.normalize_u16(depth))

@@ -24,6 +24,7 @@ namespace {
 #endif
 constexpr int TXW = 32;       // window columns per block (one warp each); TXW - 2R of them are output columns
 constexpr int PADL = 32;      // front padding (elements) of the reversed right-image rows
+constexpr int LPAD = 4;       // front padding (columns) of the left-image rows: a strip's halo may start R columns left of column 0 (minDisparity < 0)
 
 // ---------------------------------------------------------------------------------------------
 // Prefilter record of one pixel: {x: sobel v | lo<<8 | hi<<16,  y: intensity v | lo<<8 | hi<<16}
@@ -84,7 +85,7 @@ __device__ __forceinline__ uint4 pack_quads(uint32_t w0, uint32_t w1)
 
 // Right image: rexp[b][y][ch][cp][w] (uint4) = quads of the reversed-order elements (2w+cp, 2w+cp+1), where
 //              element e <-> image column W-1-(e-PADL).
-// Left image:  lexp[b][y][X][ch] (uint4) = {u, -u, lo, -hi} duplicated in both halves, X < W + TXW (clamped).
+// Left image:  lexp[b][y][LPAD + X][ch] (uint4) = {u, -u, lo, -hi} duplicated in both halves, -LPAD <= X < W + TXW (clamped).
 __global__ void __launch_bounds__(256)
 k_prefilter_expand(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, size_t gpitch, size_t gstride,
                    int W, int H, int ftzero, uint4* __restrict__ rexp, int wpw, uint4* __restrict__ lexp)
@@ -99,10 +100,10 @@ k_prefilter_expand(const uint8_t* __restrict__ left, const uint8_t* __restrict__
     const uint8_t* imgR = right + (size_t)b * gstride;
     const uint8_t* imgL = left + (size_t)b * gstride;
     const int xmax = W - 1 - (2 * t0 - PADL);      // column of element 2*t0 (the block's right-most one)
-    const int lb = min(t0 - 1, W - 2);             // blocks past the image only repeat its last column
+    const int lb = min(max(t0 - LPAD, 0) - 1, W - 2);   // first staged left column (element t <-> column clamp(t - LPAD)); blocks past the image only repeat its last column
     if (t0 < wpw)
         for (int i = threadIdx.x; i < NRC; i += 256) pr[i] = (uint16_t)prefilter_packed(imgR, gpitch, W, H, xmax + 1 - i, y, ftzero);
-    if (t0 < W + TXW)
+    if (t0 < W + TXW + LPAD)
         for (int i = threadIdx.x; i < NLC; i += 256) pl[i] = (uint16_t)prefilter_packed(imgL, gpitch, W, H, lb + i, y, ftzero);
     __syncthreads();
     if (t < wpw) {
@@ -117,10 +118,10 @@ k_prefilter_expand(const uint8_t* __restrict__ left, const uint8_t* __restrict__
         base[2 * (size_t)wpw] = pack_quads(rec[0].y, rec[1].y);    // channel 1 (intensity)
         base[3 * (size_t)wpw] = pack_quads(rec[1].y, rec[2].y);
     }
-    if (t < W + TXW) {
-        const int i = min(t, W - 1) - lb;                           // columns past the image repeat the last one
+    if (t < W + TXW + LPAD) {
+        const int i = min(max(t - LPAD, 0), W - 1) - lb;            // columns outside the image repeat the border one
         const uint2 rec = rec_from_packed(pl[i - 1], pl[i], pl[i + 1]);
-        uint4* o = lexp + ((size_t)(b * H + y) * (W + TXW) + t) * 2;
+        uint4* o = lexp + ((size_t)(b * H + y) * (W + TXW + LPAD) + t) * 2;
         o[0] = pack_quads(rec.x, rec.x);
         o[1] = pack_quads(rec.y, rec.y);
     }
@@ -176,7 +177,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity)
 template <int NR, int R, bool PAD>
 __global__ void __launch_bounds__(TXW * 32)
 k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, uint32_t* __restrict__ C,
-       int W, int H, int W1, int band_h, int Dreal)
+       int W, int H, int W1, int band_h, int Dreal, int x0, int minD)
 {
     using SM = CostSmem<NR, R>;
     constexpr int D = 64 * NR;
@@ -195,15 +196,16 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
     const int yend = ystart + nrows;
 
     // reversed element index of the strip's right-most image column, and the first staged word of each copy
-    // image column = window column + Dreal (the real numDisparities); d in [Dreal, D) is padding
-    const int Xhi = xs - R + (TXW - 1) + Dreal;
-    const int gbase = (W - 1 - Xhi) + PADL;
+    // image column = window column + x0 (x0 = minD + Dreal, clamped at 0); disparity index d means minD + d pixels;
+    // d in [Dreal, D) is padding.  PADL covers the strip's halo columns for every minD: W - 1 - Xhi + minD >= -29.
+    const int Xhi = xs - R + (TXW - 1) + x0;
+    const int gbase = (W - 1 - Xhi + minD) + PADL;
     const int wlo0 = gbase >> 1, wlo1 = (gbase - 1) >> 1;
     // this warp's first element, its pair alignment and its first word inside the staged copy
     const int e0 = gbase + (TXW - 1 - c);
     const int copy = e0 & 1;
     const int wrel = ((e0 - copy) >> 1) - (copy ? wlo1 : wlo0);
-    const int Xl0 = xs - R + Dreal;                 // image column of warp 0 in the left image
+    const int Xl0 = xs - R + x0;                    // image column of warp 0 in the left image
 
     if (tid == 0) {
 #pragma unroll
@@ -228,7 +230,7 @@ k_cost(const uint4* __restrict__ rexp, int wpw, const uint4* __restrict__ lexp, 
         if (part != 0) {
             bulk_g2s(&sm.rbuf[st][1][0][0], rrow + 2 * (size_t)wpw + wlo0, RB, &sm.bar[st]);
             bulk_g2s(&sm.rbuf[st][1][1][0], rrow + 3 * (size_t)wpw + wlo1, RB, &sm.bar[st]);
-            bulk_g2s(&sm.lbuf[st][0][0], lexp + ((size_t)(b * H + rr) * (W + TXW) + Xl0) * 2, LB, &sm.bar[st]);
+            bulk_g2s(&sm.lbuf[st][0][0], lexp + ((size_t)(b * H + rr) * (W + TXW + LPAD) + Xl0 + LPAD) * 2, LB, &sm.bar[st]);
         }
     };
     if (tid == 0) {
@@ -374,7 +376,7 @@ int launch_cost_nr(v3d_ctx* ctx, int batch, cudaStream_t st)
     const int W1 = ctx->W1, H = ctx->H;
     dim3 grid((W1 + (TXW - 2 * R) - 1) / (TXW - 2 * R), (H + band_h - 1) / band_h, batch), block(TXW * 32);
     kern<<<grid, block, smem, st>>>(ctx->rexp, ctx->rexp_wpw, ctx->lexp, reinterpret_cast<uint32_t*>(ctx->C),
-                                    ctx->W, H, W1, band_h, ctx->D);
+                                    ctx->W, H, W1, band_h, ctx->D, ctx->x0, ctx->minD);
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
@@ -396,13 +398,13 @@ int launch_cost_r(v3d_ctx* ctx, int batch, cudaStream_t st)
 // words per (row, channel, copy) of the expanded right image: the row itself, the front padding and room
 // for the widest staged copy (D = 256) to read past the last column
 int v3d_rexp_words(int W) { return (W + PADL) / 2 + 160; }
-int v3d_lexp_cols(int W) { return W + TXW; }
+int v3d_lexp_cols(int W) { return W + TXW + LPAD; }
 
 int v3d_launch_prefilter(v3d_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t gpitch,
                          size_t gstride, int batch, cudaStream_t st)
 {
     V3dScope scope(ctx, ST_PREFILTER, st);
-    const int n = ctx->rexp_wpw > ctx->W + TXW ? ctx->rexp_wpw : ctx->W + TXW;
+    const int n = ctx->rexp_wpw > ctx->W + TXW + LPAD ? ctx->rexp_wpw : ctx->W + TXW + LPAD;
     dim3 grid((n + 255) / 256, ctx->H, batch);
     k_prefilter_expand<<<grid, 256, 0, st>>>(left, right, gpitch, gstride, ctx->W, ctx->H, ctx->ftzero, ctx->rexp,
                                              ctx->rexp_wpw, ctx->lexp);

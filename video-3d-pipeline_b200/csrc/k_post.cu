@@ -7,7 +7,7 @@
 
 namespace {
 
-constexpr int INV = V3D_INVALID_DISP;
+// The invalid value is (minDisparity - 1) * 16 (-16 for the reference's minDisparity = 0): a kernel argument `inv`.
 
 // ---------------------------------------------------------------------------------------------
 // One block per image row.  cv2 walks x descending and keeps, for every right-image column x2, the
@@ -15,34 +15,35 @@ constexpr int INV = V3D_INVALID_DISP;
 // (minS << 16 | 0xffff - x) reproduces that independent of thread order.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_select(const uint2* __restrict__ rec, int16_t* __restrict__ raw, int W, int W1, int D, int maxdiff)
+k_select(const uint2* __restrict__ rec, int16_t* __restrict__ raw, int W, int W1, int D, int maxdiff, int x0, int minD, int inv)
 {
+    // window column x <-> image column x + x0; disparity index d <-> minD + d pixels; x0 = max(minD + D, 0)
     extern __shared__ uint32_t smem[];
     uint32_t* key = smem;                                   // [W]
     int16_t* d16row = reinterpret_cast<int16_t*>(smem + W); // [W]
     const size_t row = blockIdx.x;
     rec += row * W1;
     raw += row * W;
-    for (int X = threadIdx.x; X < W; X += blockDim.x) { key[X] = 0xffffffffu; d16row[X] = (int16_t)INV; }
+    for (int X = threadIdx.x; X < W; X += blockDim.x) { key[X] = 0xffffffffu; d16row[X] = (int16_t)inv; }
     __syncthreads();
     for (int x = threadIdx.x; x < W1; x += blockDim.x) {
         const uint2 r = __ldg(rec + x);
         const uint32_t best = r.x >> 16;
         if (best == 0xffffu) continue;                      // failed the uniqueness test
         const int minS = (int)(r.x & 0xffffu);
-        atomicMin(&key[x + D - (int)best], ((uint32_t)minS << 16) | (0xffffu - (uint32_t)x));
-        int d16 = (int)best * 16;
+        atomicMin(&key[x + x0 - minD - (int)best], ((uint32_t)minS << 16) | (0xffffu - (uint32_t)x));
+        int d16 = ((int)best + minD) * 16;
         if (best > 0 && (int)best < D - 1) {
             const int sm1 = (int)(r.y & 0xffffu), sp1 = (int)(r.y >> 16);
             const int den = max(sm1 + sp1 - 2 * minS, 1);
             d16 += ((sm1 - sp1) * 16 + den) / (den * 2);    // C truncating division
         }
-        d16row[x + D] = (int16_t)d16;
+        d16row[x + x0] = (int16_t)d16;
     }
     __syncthreads();
     for (int X = threadIdx.x; X < W; X += blockDim.x) {
         int d1 = d16row[X];
-        if (X >= D && d1 != INV) {
+        if (d1 != inv) {                                     // (columns outside the window kept the initial value)
             const int dl = d1 >> 4, dh = (d1 + 15) >> 4;
             const int xl = X - dl, xh = X - dh;
             bool bad = true;
@@ -50,10 +51,10 @@ k_select(const uint2* __restrict__ rec, int16_t* __restrict__ raw, int W, int W1
                 bool t = false;
                 if (xl >= 0 && xl < W) {
                     const uint32_t k = key[xl];
-                    if (k != 0xffffffffu) {
-                        const int d2 = (int)(0xffffu - (k & 0xffffu)) + D - xl;
-                        t = abs(d2 - dl) > maxdiff;
-                    }
+                    // a column nobody voted for holds cv2's initial value, the SCALED invalid disparity (minD - 1) * 16,
+                    // which passes cv2's "disp2 >= minD" test when minD >= 2 (harmless quirk at minD = 0: -16 < 0)
+                    const int d2 = k != 0xffffffffu ? (int)(0xffffu - (k & 0xffffu)) + x0 - xl : inv;
+                    t = d2 >= minD && abs(d2 - dl) > maxdiff;
                 }
                 bad = bad && t;
             }
@@ -61,14 +62,14 @@ k_select(const uint2* __restrict__ rec, int16_t* __restrict__ raw, int W, int W1
                 bool t = false;
                 if (xh >= 0 && xh < W) {
                     const uint32_t k = key[xh];
-                    if (k != 0xffffffffu) {
-                        const int d2 = (int)(0xffffu - (k & 0xffffu)) + D - xh;
-                        t = abs(d2 - dh) > maxdiff;
-                    }
+                    // a column nobody voted for holds cv2's initial value, the SCALED invalid disparity (minD - 1) * 16,
+                    // which passes cv2's "disp2 >= minD" test when minD >= 2 (harmless quirk at minD = 0: -16 < 0)
+                    const int d2 = k != 0xffffffffu ? (int)(0xffffu - (k & 0xffffu)) + x0 - xh : inv;
+                    t = d2 >= minD && abs(d2 - dh) > maxdiff;
                 }
                 bad = bad && t;
             }
-            if (bad) d1 = INV;
+            if (bad) d1 = inv;
         }
         raw[X] = (int16_t)d1;
     }
@@ -186,9 +187,9 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b)
     } while (!done);
 }
 
-__device__ __forceinline__ bool ccl_edge(int a, int b, int maxDiff)
+__device__ __forceinline__ bool ccl_edge(int a, int b, int maxDiff, int inv)
 {
-    return a != INV && b != INV && abs(a - b) <= maxDiff;
+    return a != inv && b != inv && abs(a - b) <= maxDiff;
 }
 
 // Pass 1, one block per image row: every valid pixel is labelled with the index of the first pixel
@@ -196,7 +197,7 @@ __device__ __forceinline__ bool ccl_edge(int a, int b, int maxDiff)
 // chains start one hop deep instead of a row long.
 // labels are indices into the whole batch buffer (frame b occupies [b*n, (b+1)*n))
 __global__ void __launch_bounds__(256)
-k_ccl_rows(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
+k_ccl_rows(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L, int inv,
            int* __restrict__ sizes, int W, int H, int maxDiff)
 {
     __shared__ int wmax[8];
@@ -212,7 +213,7 @@ k_ccl_rows(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, 
         int start = -1;
         if (x < W) {
             const int v = d[x];
-            const bool left = x > 0 && ccl_edge(v, d[x - 1], maxDiff);
+            const bool left = x > 0 && ccl_edge(v, d[x - 1], maxDiff, inv);
             if (!left) start = x;                     // a run (or an invalid pixel) starts here
         }
 #pragma unroll
@@ -229,7 +230,7 @@ k_ccl_rows(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, 
         // run length, accumulated at the run head (sizes[] was zeroed before the launch): one atomic per
         // stretch of equal `start` inside a warp; invalid pixels are their own start and count nothing
         {
-            const bool valid = x < W && d[x] != INV;
+            const bool valid = x < W && d[x] != inv;
             const int key = valid ? start : -2 - (int)threadIdx.x;
             const int prev = __shfl_up_sync(V3D_FULL_MASK, key, 1);
             const bool head = lane == 0 || key != prev;
@@ -250,7 +251,7 @@ k_ccl_rows(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, 
 // one per 256 pixels).  Threads whose 8 pixels lie in one run aggregate their length over the warp (one atomic
 // per stretch of such threads); the others add their own stretches.
 __global__ void __launch_bounds__(256)
-k_ccl_rows_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
+k_ccl_rows_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L, int inv,
               int* __restrict__ sizes, int W, int H, int maxDiff)
 {
     __shared__ int wmax[8];
@@ -265,11 +266,11 @@ k_ccl_rows_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_
     if (act) {
         const uint4 q = __ldg(reinterpret_cast<const uint4*>(d + x0));
         const uint32_t w[4] = { q.x, q.y, q.z, q.w };
-        int pl = x0 > 0 ? (int)__ldg(d + x0 - 1) : INV;
+        int pl = x0 > 0 ? (int)__ldg(d + x0 - 1) : inv;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             v[i] = (int16_t)(w[i >> 1] >> ((i & 1) * 16));
-            if (!ccl_edge(v[i], pl, maxDiff)) cur = x0 + i;      // a run (or an invalid pixel) starts here
+            if (!ccl_edge(v[i], pl, maxDiff, inv)) cur = x0 + i;      // a run (or an invalid pixel) starts here
             st[i] = cur;
             pl = v[i];
         }
@@ -291,7 +292,7 @@ k_ccl_rows_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             if (st[i] < 0) st[i] = pre;
-            uniform = uniform && v[i] != INV && st[i] == st[0];
+            uniform = uniform && v[i] != inv && st[i] == st[0];
         }
         int4* lp = reinterpret_cast<int4*>(L + rowbase + x0);
         lp[0] = make_int4(rowbase + st[0], rowbase + st[1], rowbase + st[2], rowbase + st[3]);
@@ -312,7 +313,7 @@ k_ccl_rows_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_
         int s = -1, len = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            if (v[i] == INV) continue;
+            if (v[i] == inv) continue;
             if (st[i] != s) {
                 if (len) atomicAdd(&sizes[rowbase + s], len);
                 s = st[i]; len = 0;
@@ -326,7 +327,7 @@ k_ccl_rows_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_
 // Pass 2: vertical unions.  A union is skipped when the pixel's left neighbour already carries it
 // (x-1,y)~(x,y), (x-1,y-1)~(x,y-1) and (x-1,y)~(x-1,y-1) all hold.
 __global__ void __launch_bounds__(256)
-k_ccl_merge(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
+k_ccl_merge(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L, int inv,
             int W, int H, int maxDiff)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
@@ -334,10 +335,10 @@ k_ccl_merge(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e,
     const int16_t* d = disp + (size_t)b * dstride_e;
     const int v = d[(size_t)y * dpitch_e + x];
     const int u = d[(size_t)(y - 1) * dpitch_e + x];
-    if (!ccl_edge(v, u, maxDiff)) return;
+    if (!ccl_edge(v, u, maxDiff, inv)) return;
     if (x > 0) {
         const int vl = d[(size_t)y * dpitch_e + x - 1], ul = d[(size_t)(y - 1) * dpitch_e + x - 1];
-        if (ccl_edge(v, vl, maxDiff) && ccl_edge(u, ul, maxDiff) && ccl_edge(vl, ul, maxDiff)) return;
+        if (ccl_edge(v, vl, maxDiff, inv) && ccl_edge(u, ul, maxDiff, inv) && ccl_edge(vl, ul, maxDiff, inv)) return;
     }
     const int i = (b * H + y) * W + x;
     uf_union(L, i, i - W);
@@ -346,7 +347,7 @@ k_ccl_merge(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e,
 // The same pass on 8 pixels per thread (128-bit loads of both rows; the left neighbours of a pixel are the
 // previous loop iteration's values).
 __global__ void __launch_bounds__(256)
-k_ccl_merge_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L,
+k_ccl_merge_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, int* __restrict__ L, int inv,
                int W, int H, int maxDiff, int n_groups)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -360,13 +361,13 @@ k_ccl_merge_v8(const int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride
     const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(r1)), q0 = __ldg(reinterpret_cast<const uint4*>(r0));
     const uint32_t w1[4] = { q1.x, q1.y, q1.z, q1.w }, w0[4] = { q0.x, q0.y, q0.z, q0.w };
     bool has_left = x0 > 0;
-    int vl = has_left ? (int)__ldg(r1 - 1) : INV, ul = has_left ? (int)__ldg(r0 - 1) : INV;
+    int vl = has_left ? (int)__ldg(r1 - 1) : inv, ul = has_left ? (int)__ldg(r0 - 1) : inv;
     const int base = row * W + x0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int v = (int16_t)(w1[i >> 1] >> ((i & 1) * 16)), u = (int16_t)(w0[i >> 1] >> ((i & 1) * 16));
-        if (ccl_edge(v, u, maxDiff)) {
-            const bool covered = has_left && ccl_edge(v, vl, maxDiff) && ccl_edge(u, ul, maxDiff) && ccl_edge(vl, ul, maxDiff);
+        if (ccl_edge(v, u, maxDiff, inv)) {
+            const bool covered = has_left && ccl_edge(v, vl, maxDiff, inv) && ccl_edge(u, ul, maxDiff, inv) && ccl_edge(vl, ul, maxDiff, inv);
             if (!covered) uf_union(L, base + i, base + i - W);
         }
         vl = v; ul = u; has_left = true;
@@ -396,7 +397,7 @@ k_ccl_apply(int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, const
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
     int16_t* p = disp + (size_t)b * dstride_e + (size_t)y * dpitch_e + x;
-    if (*p == INV) return;
+    if (*p == newVal) return;                        // newVal is the invalid value itself
     const int root = L[L[(b * H + y) * W + x]];      // pixel -> run head -> root (heads were flattened by k_ccl_count)
     if (sizes[root] <= maxSize) *p = (int16_t)newVal;
 }
@@ -415,7 +416,7 @@ k_ccl_apply_v8(int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, co
     uint4* p = reinterpret_cast<uint4*>(disp + (size_t)b * dstride_e + (size_t)y * dpitch_e + x0);
     const uint4 q = *p;
     uint32_t w[4] = { q.x, q.y, q.z, q.w };
-    const uint32_t inv2 = ((uint32_t)(uint16_t)INV << 16) | (uint16_t)INV;
+    const uint32_t inv2 = ((uint32_t)(uint16_t)newVal << 16) | (uint16_t)newVal;   // newVal is the invalid value itself
     if (q.x == inv2 && q.y == inv2 && q.z == inv2 && q.w == inv2) return;
     const int4* lp = reinterpret_cast<const int4*>(L + (size_t)row * W + x0);      // row * W + x0 is a multiple of 8
     const int4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
@@ -425,7 +426,7 @@ k_ccl_apply_v8(int16_t* __restrict__ disp, size_t dpitch_e, size_t dstride_e, co
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int16_t v = (int16_t)(w[i >> 1] >> ((i & 1) * 16));
-        if (v == INV) continue;
+        if (v == (int16_t)newVal) continue;
         if (lab[i] != prev) {
             prev = lab[i];
             kill = sizes[L[prev]] <= maxSize;      // run head -> root (flattened by k_ccl_count) -> component size
@@ -618,7 +619,7 @@ int v3d_launch_select(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     V3dScope scope(ctx, ST_SELECT, st);
     const size_t smem = (size_t)ctx->W * 4 + (size_t)ctx->W * 2 + 16;
-    k_select<<<batch * ctx->H, 256, smem, st>>>(ctx->rec, ctx->raw, ctx->W, ctx->W1, ctx->D, ctx->maxdiff);
+    k_select<<<batch * ctx->H, 256, smem, st>>>(ctx->rec, ctx->raw, ctx->W, ctx->W1, ctx->D, ctx->maxdiff, ctx->x0, ctx->minD, ctx->inv);
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;
 }
@@ -647,18 +648,18 @@ int v3d_launch_speckle(v3d_ctx* ctx, int batch, int16_t* disp, size_t dpitch, si
     const int n_total = batch * W * H;
     V3D_CUDA(cudaMemsetAsync(ctx->sizes, 0, (size_t)n_total * sizeof(int), st));
     const bool vec = vec8_ok(disp, dpitch / 2, dstride / 2, W);
-    if (vec && W <= 2048) k_ccl_rows_v8<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H, maxDiff);
-    else k_ccl_rows<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H, maxDiff);
+    if (vec && W <= 2048) k_ccl_rows_v8<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->inv, ctx->sizes, W, H, maxDiff);
+    else k_ccl_rows<<<batch * H, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->inv, ctx->sizes, W, H, maxDiff);
     const int n_groups = vec ? batch * H * (W / 8) : 0;
-    if (vec) k_ccl_merge_v8<<<(n_groups + 255) / 256, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff, n_groups);
-    else k_ccl_merge<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, W, H, maxDiff);
+    if (vec) k_ccl_merge_v8<<<(n_groups + 255) / 256, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->inv, W, H, maxDiff, n_groups);
+    else k_ccl_merge<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->inv, W, H, maxDiff);
     k_ccl_count<<<(n_total + 255) / 256, 256, 0, st>>>(ctx->labels, ctx->sizes, n_total);
     if (vec) {
         k_ccl_apply_v8<<<(n_groups + 255) / 256, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H,
-                                                               ctx->p.speckleWindowSize, (ctx->p.minDisparity - 1) * 16, n_groups);
+                                                               ctx->p.speckleWindowSize, ctx->inv, n_groups);
     } else {
         k_ccl_apply<<<grid, 256, 0, st>>>(disp, dpitch / 2, dstride / 2, ctx->labels, ctx->sizes, W, H,
-                                          ctx->p.speckleWindowSize, (ctx->p.minDisparity - 1) * 16);
+                                          ctx->p.speckleWindowSize, ctx->inv);
     }
     V3D_LAUNCHED(ctx, 4);
     return V3D_OK;

@@ -91,7 +91,9 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     if (!params || !out) return v3d_fail(V3D_EINVAL, "null argument");
     *out = nullptr;
     const v3d_sgbm_params& p = *params;
-    if (p.minDisparity != 0) return v3d_fail(V3D_EINVAL, "minDisparity must be 0 (depth.py:316)");
+    // (minDisparity + numDisparities) * 16 and (minDisparity - 1) * 16 must fit the int16 output
+    if (p.minDisparity < -1024 || p.minDisparity > 1024)
+        return v3d_fail(V3D_EINVAL, "minDisparity %d unsupported (-1024 .. 1024; depth.py:316 uses 0)", p.minDisparity);
     if (p.numDisparities < 16 || p.numDisparities > 256 || (p.numDisparities % 16))     // cv2: positive multiple of 16
         return v3d_fail(V3D_EINVAL, "numDisparities %d unsupported (multiples of 16 up to 256)", p.numDisparities);
     if (p.blockSize < 1 || !(p.blockSize & 1) || p.blockSize > 7)
@@ -102,9 +104,11 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     if (eye_w > 8192) return v3d_fail(V3D_EINVAL, "eye width %d too large (k_select keeps a row in shared memory)", eye_w);
     if ((long long)max_batch * eye_w * eye_h >= (1ll << 31))
         return v3d_fail(V3D_EINVAL, "max_batch * width * height must stay below 2^31 (32-bit pixel labels)");
-    if (eye_w - p.numDisparities <= p.blockSize / 2)   // cv2.error in stereosgbm.cpp
-        return v3d_fail(V3D_EINVAL, "eye width %d too small for numDisparities %d (cv2 raises here)", eye_w,
-                        p.numDisparities);
+    // the window of image columns that have every disparity: [max(minD + D, 0), W + min(minD, 0))  (OpenCV minX1, maxX1)
+    const int win_x0 = std::max(p.minDisparity + p.numDisparities, 0), win_x1 = eye_w + std::min(p.minDisparity, 0);
+    if (win_x1 - win_x0 <= p.blockSize / 2)            // cv2.error in stereosgbm.cpp (for minDisparity = 0: W - D <= blockSize / 2)
+        return v3d_fail(V3D_EINVAL, "eye width %d too small for numDisparities %d, minDisparity %d (cv2 raises here)", eye_w,
+                        p.numDisparities, p.minDisparity);
     if (p.preFilterCap < 0 || p.preFilterCap > 63) return v3d_fail(V3D_EINVAL, "preFilterCap out of range");
     if (p.uniquenessRatio > 100) return v3d_fail(V3D_EINVAL, "uniquenessRatio out of range");
     const int P1 = p.P1 > 0 ? p.P1 : 2;
@@ -127,7 +131,8 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     v3d_ctx* c = new (std::nothrow) v3d_ctx();
     if (!c) return v3d_fail(V3D_ENOMEM, "host allocation failed");
     c->device = device; c->p = p;
-    c->W = eye_w; c->H = eye_h; c->D = p.numDisparities; c->W1 = eye_w - c->D; c->R = p.blockSize / 2;
+    c->W = eye_w; c->H = eye_h; c->D = p.numDisparities; c->W1 = win_x1 - win_x0; c->R = p.blockSize / 2;
+    c->minD = p.minDisparity; c->x0 = win_x0; c->inv = (p.minDisparity - 1) * 16;
     c->Dk = c->D <= 64 ? 64 : (c->D <= 128 ? 128 : 256);
     c->max_batch = max_batch; c->ndirs = ndirs;
     c->P1 = P1; c->P2 = P2;

@@ -30,6 +30,7 @@ struct v3d_ctx {
     int device;
     v3d_sgbm_params p;
     int W, H, D, W1, R, max_batch, ndirs;
+    int minD, x0, inv;           // minDisparity; first image column of the window, max(minD + D, 0); invalid value (minD - 1) * 16
     int Dk;                      // disparities the kernels are instantiated for (64/128/256 >= D); d in [D, Dk) is padding
     int P1, P2, uniq, maxdiff, ftzero;
 

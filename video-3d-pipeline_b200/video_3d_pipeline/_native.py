@@ -285,7 +285,8 @@ class Context:
 
     def debug_tap(self, which, batch):
         """Copy of a workspace volume of the last compute call (parity tests only)."""
-        W1 = self.W - self.D
+        md = int(self.params.minDisparity)
+        W1 = (self.W + min(md, 0)) - max(md + self.D, 0)          # OpenCV: maxX1 - minX1
         shape, dt = {0: ((batch, self.H, W1, self.Dk), torch.int16), 1: ((batch, self.H, W1, self.Dk), torch.int16),
                      2: ((batch, self.H, self.W), torch.int16), 3: ((batch, self.H, self.W), torch.int16)}[which]
         out = torch.empty(shape, dtype=dt, device=self.device)

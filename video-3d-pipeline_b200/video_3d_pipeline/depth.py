@@ -44,6 +44,7 @@ class HybridStereoDepthExtractor:
                  unsqueeze_sbs: bool = True,
                  num_disparities: int = 64,
                  sgbm_mode: int = _native.MODE_SGBM,
+                 min_disparity: int = 0,
                  num_gpus: int = 1,
                  gpu_index: int = 0,
                  decode_threads: int = 4,
@@ -63,6 +64,7 @@ class HybridStereoDepthExtractor:
         self.unsqueeze_sbs = unsqueeze_sbs
         self.num_disparities = int(num_disparities)
         self.sgbm_mode = int(sgbm_mode)
+        self.min_disparity = int(min_disparity)        # depth.py:316 literal 0
         self.num_gpus = int(num_gpus)
         self.gpu_index = int(gpu_index)
         self.decode_threads = int(decode_threads)      # host pipeline knobs
@@ -113,7 +115,7 @@ class HybridStereoDepthExtractor:
 
     def sgbm_params(self) -> _native.SgbmParams:
         """The literals of depth.py:315-325 with D / mode from the constructor."""
-        return _native.SgbmParams(numDisparities=self.num_disparities, mode=self.sgbm_mode)
+        return _native.SgbmParams(numDisparities=self.num_disparities, mode=self.sgbm_mode, minDisparity=self.min_disparity)
 
     def _context(self, eye_w: int, eye_h: int, batch: int, lane: int = 0) -> _native.Context:
         c = self._lane_ctx.get(lane)
@@ -136,6 +138,8 @@ class HybridStereoDepthExtractor:
         nd, mode = getattr(self, "num_disparities", 64), getattr(self, "sgbm_mode", _native.MODE_SGBM)
         if nd != 64 or mode != _native.MODE_SGBM:                 # depth.py:317 / cv2 default mode
             key += f"_D{nd}m{mode}"
+        if getattr(self, "min_disparity", 0) != 0:                # depth.py:316
+            key += f"_min{self.min_disparity}"
         if getattr(self, "depth_scale", "frame") != "frame":
             key += f"_{self.depth_scale}{nd}"
         if getattr(self, "_guidance_ignored", False):             # never share a directory with DPT-blended maps
