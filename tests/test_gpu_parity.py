@@ -467,3 +467,15 @@ def test_min_disparity_matches_cv2(minD, W, H, D, mode):
         depth[depth <= 0] = 0
         assert np.array_equal(f32[0].cpu().numpy(), depth)
         assert np.array_equal(_u16(u16)[0], cv2_chain.normalize_u16(depth))
+
+
+def test_very_wide_rows_match_cv2():
+    """Eye widths beyond 8192 columns (the disparity-selection kernel keeps a row of votes in shared memory, opted in
+    above 48 KB; the speckle filter, the per-direction vertical kernels and the cost strips take their generic paths)."""
+    for (W, H, D, mode) in ((9000, 3, 64, 0), (12345, 2, 128, 1)):
+        left, right, _ = synthetic.stereo_pair(17, 0, W, H, D)
+        with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=mode)) as ctx:
+            d = ctx.sgbm_compute(torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda())[0].cpu().numpy()
+        assert np.array_equal(d, cv2_chain.make_matcher(D, mode).compute(left, right)), (W, H, D, mode)
+    with pytest.raises(ValueError):
+        nv.Context(40000, 2, nv.SgbmParams())

@@ -618,7 +618,11 @@ int v3d_launch_normalize_f32(v3d_ctx* ctx, const float* in, size_t n, int batch,
 int v3d_launch_select(v3d_ctx* ctx, int batch, cudaStream_t st)
 {
     V3dScope scope(ctx, ST_SELECT, st);
-    const size_t smem = (size_t)ctx->W * 4 + (size_t)ctx->W * 2 + 16;
+    const size_t smem = (size_t)ctx->W * 4 + (size_t)ctx->W * 2 + 16;      // one row of votes and disparities
+    if (smem > 48 * 1024 && !ctx->select_attr_set) {
+        V3D_CUDA(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->select_attr_set = 1;
+    }
     k_select<<<batch * ctx->H, 256, smem, st>>>(ctx->rec, ctx->raw, ctx->W, ctx->W1, ctx->D, ctx->maxdiff, ctx->x0, ctx->minD, ctx->inv);
     V3D_LAUNCHED(ctx, 1);
     return V3D_OK;

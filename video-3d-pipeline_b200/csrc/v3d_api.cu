@@ -101,7 +101,7 @@ int v3d_create(int device, const v3d_sgbm_params* params, int eye_w, int eye_h, 
     if (p.mode != V3D_MODE_SGBM && p.mode != V3D_MODE_HH)
         return v3d_fail(V3D_EINVAL, "mode %d unsupported (0 = SGBM, 1 = HH)", p.mode);
     if (eye_w <= 0 || eye_h <= 0 || max_batch <= 0) return v3d_fail(V3D_EINVAL, "bad size");
-    if (eye_w > 8192) return v3d_fail(V3D_EINVAL, "eye width %d too large (k_select keeps a row in shared memory)", eye_w);
+    if (eye_w > 32768) return v3d_fail(V3D_EINVAL, "eye width %d too large (k_select keeps a row in shared memory: 6 bytes per column)", eye_w);
     if ((long long)max_batch * eye_w * eye_h >= (1ll << 31))
         return v3d_fail(V3D_EINVAL, "max_batch * width * height must stay below 2^31 (32-bit pixel labels)");
     // the window of image columns that have every disparity: [max(minD + D, 0), W + min(minD, 0))  (OpenCV minX1, maxX1)

@@ -73,6 +73,7 @@ struct v3d_ctx {
     int v3_cl;               // CTAs per cluster the fused sweep runs with on this device (0 = not chosen yet)
     int no_fused_vertical;
     int h_attr_set;
+    int select_attr_set;
     unsigned long long cost_attr_set;   // test hook: force the one-direction-per-launch path kernels
     std::vector<V3dTimedSpan> spans;
     double stage_ms[ST_COUNT];
