@@ -119,7 +119,7 @@ k_path_lr_ckpt(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ ckpt, int
 // 4-lane reductions per CHUNK.  S_total never returns to memory.
 // ------------------------------------------------------------------------------------------
 template <int NR, bool TAP_S, bool PAD>
-__global__ void __launch_bounds__(HW_WARPS * 32)
+__global__ void __launch_bounds__(HW_WARPS * 32, NR <= 2 ? 3 : 1)      // 3 blocks per SM by shared memory: up to 80 registers
 k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, const uint16_t* __restrict__ ckpt,
                   uint2* __restrict__ rec, int W1, int rows, uint32_t P1p, uint32_t P2p, int uniq, int Dreal)
 {
@@ -188,6 +188,9 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
             for (int r = 0; r < NR; r++) Ml[r] = 0;
         }
         if (n == CH) {
+            // Steps 0..3 keep their two L in registers; steps 4..7 meet the pixels the other direction has already
+            // visited, so every pixel's S is read and written ONCE (S + L_left-to-right + L_right-to-left).
+            uint32_t keepA[CH / 2][NR], keepB[CH / 2][NR];
 #pragma unroll
             for (int i = 0; i < CH; i++) {
                 const int j = CH - 1 - i;
@@ -196,14 +199,19 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
                 unpack<NR>(cs[j * 32], Cb);
                 path_step<NR>(Ml, Ca, La, P1p, P2p, lane);       // left to right at pixel i
                 path_step<NR>(M, Cb, Lb, P1p, P2p, lane);        // right to left at pixel 7 - i
-                unpack<NR>(ss[i * 32], Sa);
+                if (i < CH / 2) {
 #pragma unroll
-                for (int r = 0; r < NR; r++) Sa[r] += La[r];
-                ss[i * 32] = pack<NR>(Sa);
-                unpack<NR>(ss[j * 32], Sb);                      // (i and j never coincide: CH is even)
+                    for (int r = 0; r < NR; r++) { keepA[i][r] = La[r]; keepB[i][r] = Lb[r]; }
+                } else {
+                    unpack<NR>(ss[i * 32], Sa);                  // pixel i: right-to-left was here at step 7 - i = j
 #pragma unroll
-                for (int r = 0; r < NR; r++) Sb[r] += Lb[r];
-                ss[j * 32] = pack<NR>(Sb);
+                    for (int r = 0; r < NR; r++) Sa[r] += La[r] + keepB[j][r];
+                    ss[i * 32] = pack<NR>(Sa);
+                    unpack<NR>(ss[j * 32], Sb);                  // pixel j: left-to-right was here at step j
+#pragma unroll
+                    for (int r = 0; r < NR; r++) Sb[r] += Lb[r] + keepA[j][r];
+                    ss[j * 32] = pack<NR>(Sb);
+                }
             }
         } else {
             for (int j = 0; j < n; j++) {
