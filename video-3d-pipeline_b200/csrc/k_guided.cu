@@ -526,7 +526,10 @@ k_guided_apply_s(const float4* __restrict__ ab, const uint8_t* __restrict__ guid
     }
 }
 
-constexpr int SNT = 128, SR = 4, SGR = 8;
+#ifndef V3D_GUIDED_ANT
+#define V3D_GUIDED_ANT 128
+#endif
+constexpr int SNT = V3D_GUIDED_ANT, SR = 4, SGR = 8;      // SNT: threads (= region columns) per CTA of the apply kernel
 #ifndef V3D_GUIDED_CGR
 #define V3D_GUIDED_CGR 8
 #endif
