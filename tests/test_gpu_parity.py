@@ -479,3 +479,28 @@ def test_very_wide_rows_match_cv2():
         assert np.array_equal(d, cv2_chain.make_matcher(D, mode).compute(left, right)), (W, H, D, mode)
     with pytest.raises(ValueError):
         nv.Context(40000, 2, nv.SgbmParams())
+
+
+def test_context_reuse_with_varying_batches_and_streams():
+    """One context, calls with different batch sizes on different streams (workspace buffers, checkpoints, side stream
+    and cluster choice are per context and must not leak state between calls)."""
+    W, H, D, B = 520, 48, 128, 5
+    frames = np.stack([synthetic.sbs_frame(60, t, W, H, D) for t in range(B)])
+    m = cv2_chain.make_matcher(D, 1)
+    refs = []
+    for b in range(B):
+        l, r = cv2_chain.split_sbs_frame(frames[b], False)
+        refs.append(m.compute(cv2_chain.to_gray(l), cv2_chain.to_gray(r)))
+    dev = torch.from_numpy(frames).cuda()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    with nv.Context(W, H, nv.SgbmParams(numDisparities=D, mode=1), max_batch=B) as ctx:
+        for k, (lo, n) in enumerate(((0, 5), (3, 2), (1, 4), (4, 1), (0, 3))):
+            with torch.cuda.stream(streams[k % 2]):
+                streams[k % 2].wait_stream(torch.cuda.current_stream())
+                res = ctx.depth_frames(dev[lo:lo + n].contiguous(), False, want=("disp",))
+            streams[k % 2].synchronize()
+            got = res["disp"].cpu().numpy()
+            for i in range(n):
+                assert np.array_equal(got[i], refs[lo + i]), (k, lo, n, i)
+        with pytest.raises(ValueError):
+            ctx.depth_frames(torch.zeros((B + 1, H, 2 * W, 3), dtype=torch.uint8, device="cuda"), False, want=())

@@ -1,7 +1,7 @@
 # Evidence run on a GPU box: default bench, reference arm, the other BASELINE configs, ncu launch list of the
 # default command, ncu --set full of the largest kernels.  Outputs land in gpurun_out/ and are summarised into
 # profiles/ (tools/ncu_traffic.py turns the capture into profiles/traffic_per_frame.json).
-#   gpurun -- bash tools/gpu_profile.sh [tag] [configs...]
+#   gpurun -- bash tools/gpu_profile.sh [tag] [configs...]      (tools/ab.sh: A/B of library variants on one box)
 TAG=${1:-r02}; shift
 CFGS=${@:-cfg1 cfg2 cfg3 cfg5}
 K='k_cost|k_path_vert3|k_path_lr_ckpt|k_path_rl_wta_tma|k_guided_coeff_s|k_guided_apply_s|k_prefilter_expand'
