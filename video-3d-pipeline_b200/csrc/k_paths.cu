@@ -412,7 +412,19 @@ int try_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
 #endif
     constexpr int NW = NR <= 2 ? V3D_V3_NW2 : V3D_V3_NW4;
     constexpr int CLA = NR <= 2 ? V3D_V3_CL2 : 16, CLB = NR <= 2 ? 8 : 16;     // preferred / portable cluster size
+    constexpr int CLS = NR <= 2 ? 4 : 16;                                       // small cluster for narrow frames
     int rc = V3D_OK;
+    if (!ctx->v3_cl) {
+        // Narrow frames (W1 <= 4 * NW * 8 columns: e.g. 960-wide eyes) fit the shared memory of 4 CTAs: 33 such
+        // clusters are co-resident on B200 (132 SMs) and every warp keeps 7 columns instead of 3-4, i.e. enough
+        // interior columns to run while the neighbours' edge states are in flight.
+        int ns = 0;
+        if (CLS != CLA && ctx->W1 <= CLS * NW * 8 && ctx->W1 / (CLS * NW) >= 3) {
+            const int fs = vert3_dispatch<NR, CLS, NW>(ctx, batch, sy, accum, st, &ns, rc);
+            if (rc) return rc;
+            if (fs && ns > 0) { ctx->v3_cl = CLS; ctx->max_clusters = ns; }
+        }
+    }
     if (!ctx->v3_cl) {
         int na = 0, nb = 0;
         const int fa = vert3_dispatch<NR, CLA, NW>(ctx, batch, sy, accum, st, &na, rc);
@@ -426,6 +438,10 @@ int try_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st)
             ctx->no_fused_vertical = 1;
             return 0;
         }
+    }
+    if (CLS != CLA && ctx->v3_cl == CLS) {
+        const int fit = vert3_dispatch<NR, CLS, NW>(ctx, batch, sy, accum, st, nullptr, rc);
+        return rc ? rc : fit;
     }
     const int fit = ctx->v3_cl == CLA ? vert3_dispatch<NR, CLA, NW>(ctx, batch, sy, accum, st, nullptr, rc)
                                       : vert3_dispatch<NR, CLB, NW>(ctx, batch, sy, accum, st, nullptr, rc);
