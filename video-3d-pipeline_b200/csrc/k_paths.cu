@@ -104,6 +104,30 @@ k_path_vert(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, 
 // V3_CL CTAs per cluster, V3_NW warps per CTA: 8 x 32 for D <= 128 (portable cluster size); 16 x 18 for
 // D = 256, whose 512-byte state vectors need the shared memory of 16 SMs per frame (non-portable size).
 
+// C loads of the D = 256 fused sweep (V3D_V3_D256_HINTS).  That sweep is latency-bound (18 warps per SM, about half of
+// its issue slots used, 45-53 % of its stall samples on the long scoreboard: profiles/r02e_vert3_d256_stalls.txt):
+// ptxas gives ALL global loads of the row body one scoreboard, so the row's first use of C waits for the youngest
+// outstanding load -- the one issued less than a column earlier for the last column of the next row -- and the kernel's
+// few spilled registers (the st.async target addresses, re-read every row) are evicted from L1 by the C stream.
+//   * every C value is used once: the loads do not allocate in L1 (LDG.E.NA), the spill slots stay resident;
+//   * the row after the next one is prefetched into L2 at the top of every row (CCTL.E.PF2), so that the wait is an L2
+//     hit instead of a DRAM round trip.
+// Measured on B200: the two sweeps of cfg5 7.34 -> 7.05 ms per 7 frames.  For D <= 128 (32 warps per SM, integer-pipe and
+// issue bound) the same two changes are neutral / 3 % slower (3.47 -> 3.48 / 3.59 ms), so they stay off there.
+#ifndef V3D_V3_D256_HINTS
+#define V3D_V3_D256_HINTS 1
+#endif
+template <int NR> __device__ __forceinline__ typename Vec<NR>::T ld_c(const typename Vec<NR>::T* p) { return __ldg(p); }
+#if V3D_V3_D256_HINTS
+template <> __device__ __forceinline__ uint4 ld_c<4>(const uint4* p)
+{
+    uint4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int NR, int CPW, int SMODE, int V3_CL, int V3_NW>
 __global__ void __launch_bounds__(V3_NW * 32, 1)
 k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1, int H, int sy,
@@ -115,6 +139,7 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     VT* Mst = reinterpret_cast<VT*>(v3smem);          // [3][COLS][32]   path state
     VT* inbox = Mst + 3 * COLS * 32;                  // [2][V3_NW][2][32] boundary vectors from the neighbours, double buffered
     uint64_t* mb = reinterpret_cast<uint64_t*>(inbox + 2 * V3_NW * 2 * 32);   // [2][V3_NW] one mbarrier per warp and buffer
+    uint4* nbr = reinterpret_cast<uint4*>(mb + 2 * V3_NW);                    // [V3_NW] lane 0's st.async targets {left inbox, left barrier, right inbox, right barrier}
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int frame = blockIdx.x / V3_CL;
@@ -154,7 +179,7 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         const VT* Crow = C + ((size_t)y * W1 + gcol0) * 32;
 #pragma unroll
         for (int j = 0; j < CPW; j++)
-            if (j < nv) cq[j] = __ldg(Crow + j * 32);
+            if (j < nv) cq[j] = ld_c<NR>(Crow + j * 32);
     }
     VT* Md = Mst + (0 * COLS + lc0) * 32 + lane;      // this warp's state rows, one per direction
     VT* Ml = Mst + (1 * COLS + lc0) * 32 + lane;
@@ -181,6 +206,13 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         to_r = mapa_u32(smem_u32(inbox + (nw * 2 + 0) * 32 + lane), nr);
         to_r_bar = mapa_u32(smem_u32(mb + nw), nr);
     }
+    // The four cluster addresses are needed once per row and would otherwise be the registers ptxas spills to local
+    // memory (the kernel sits on its register cap): lane 0's values live in shared memory, one broadcast LDS.128 per row
+    // brings them back (a lane's inbox slot is lane 0's plus lane * sizeof(VT): mapa only replaces the CTA bits).
+    if (lane == 0) nbr[w] = make_uint4(to_l, to_l_bar, to_r, to_r_bar);
+    __syncwarp();
+    const uint32_t nbr_addr = smem_u32(nbr + w);
+    const uint32_t lane_off = (uint32_t)lane * (uint32_t)sizeof(VT);
     // One column: the three path steps, the state write-back and the S store.  inl / inr are the previous
     // row's states arriving from the left / right neighbour column.
     auto do_col = [&](int j, const uint32_t (&inl)[NR], const uint32_t (&inr)[NR], bool more, const VT* Cnext,
@@ -189,7 +221,7 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         unpack<NR>(cq[j], Cr);
         // next row's C (on the last row Cnext points at the current row again: an unconditional load goes
         // straight into cq, a predicated one costs a dependent move that waits for it)
-        cq[j] = __ldg(Cnext + j * 32);
+        cq[j] = ld_c<NR>(Cnext + j * 32);
         unpack<NR>(Md[j * 32], M);                               // (x, y-sy)
         path_step<NR>(M, Cr, L, P1p, P2p, lane);
         Md[j * 32] = pack<NR>(M);
@@ -228,12 +260,25 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         const VT* Cnext = C + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
         VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
         const VT* Snext = S + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
+#if V3D_V3_D256_HINTS
+        if constexpr (NR == 4) {
+            // row i + 2 (clamped to the last row: a redundant prefetch is cheaper than a branch)
+            const int y2 = sy > 0 ? min(i + 2, H - 1) : max(H - 3 - i, 0);
+            const VT* C2 = C + ((size_t)y2 * W1 + gcol0) * 32;
+#pragma unroll
+            for (int j = 0; j < CPW; j++)
+                if (j < nv) prefetch_l2(C2 + j * 32);
+        }
+#endif
         const uint32_t phase = (i >> 1) & 1;
         V3D_DASSERT(par == 0 || par == 1);                               // double-buffered inboxes: [par][warp][side]
         V3D_DASSERT((char*)(in_r + par * PARSTRIDE) + sizeof(VT) <= (char*)mb && y >= 0 && y < H);
         // (a warp with a right neighbour is full unless the columns are balanced; a compile-time index where possible)
-        if (has_right) st_async(to_r + par * PARSTRIDE * (uint32_t)sizeof(VT), Ml[((NR <= 2 && CPW >= 4 ? nv : CPW) - 1) * 32], to_r_bar + par * V3_NW * 8);
-        if (has_left) st_async(to_l + par * PARSTRIDE * (uint32_t)sizeof(VT), Mr[0], to_l_bar + par * V3_NW * 8);
+        uint4 nb;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(nb.x), "=r"(nb.y), "=r"(nb.z), "=r"(nb.w) : "r"(nbr_addr));
+        const uint32_t par_off = lane_off + par * PARSTRIDE * (uint32_t)sizeof(VT);
+        if (has_right) st_async(nb.z + par_off, Ml[((NR <= 2 && CPW >= 4 ? nv : CPW) - 1) * 32], nb.w + par * V3_NW * 8);
+        if (has_left) st_async(nb.x + par_off, Mr[0], nb.y + par * V3_NW * 8);
         if (lane == 0 && rx_bytes) mbar_expect_tx(my_bar + par * V3_NW, rx_bytes);
         // A warp with NV >= 3 columns: the interior columns need nothing from other warps, so they run between the
         // barrier's arrive and wait; only the two edge columns wait for the neighbours' states.
@@ -341,7 +386,7 @@ template <int NR, int CPW, int V3_CL, int V3_NW>
 int launch_vert3(v3d_ctx* ctx, int batch, int sy, bool accum, cudaStream_t st, int* query)
 {
     using VT = typename Vec<NR>::T;
-    const size_t smem = ((size_t)3 * V3_NW * CPW * 32 + (size_t)2 * V3_NW * 2 * 32) * sizeof(VT) + (size_t)2 * V3_NW * 8;
+    const size_t smem = ((size_t)3 * V3_NW * CPW * 32 + (size_t)2 * V3_NW * 2 * 32) * sizeof(VT) + (size_t)2 * V3_NW * 8 + (size_t)V3_NW * 16;
     auto kw = k_path_vert3<NR, CPW, S_WRITE, V3_CL, V3_NW>;
     auto ka = k_path_vert3<NR, CPW, S_ACCUM, V3_CL, V3_NW>;
     V3D_CUDA(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
