@@ -153,8 +153,19 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     constexpr bool CAN_BALANCE = NR <= 2;           // (D = 256 never balances: see launch_vert3)
     const int gcol0 = (CAN_BALANCE && balanced) ? (int)((long long)gw_ * W1 / NWT) : gw_ * CPW;       // first column this warp owns
     const int lc0 = w * CPW;
-    const VT* C = reinterpret_cast<const VT*>(Cv) + (size_t)frame * H * W1 * 32 + lane;
-    VT* S = reinterpret_cast<VT*>(Sv) + (size_t)frame * H * W1 * 32 + lane;
+    // Addresses.  WALK: the kernel parameters stay in the constant bank and ONE 64-bit element offset walks down (or up)
+    // the rows -- the row top is two wide adds instead of two 64-bit multiplies and there are no row-invariant base
+    // pointers to spill (D = 256: the last spills go, 7.06 -> 6.93 ms per 7 frames of cfg5; D = 64: 2.62 -> 2.59 ms).
+    // At D = 128 ptxas turns the same source into a body that re-reads spilled values in the middle of a row
+    // (3.38 -> 3.68 ms), so that instantiation keeps the frame pointers and multiplies the row index.
+#ifndef V3D_V3_WALK2
+#define V3D_V3_WALK2 0
+#endif
+    constexpr bool WALK = NR != 2 || V3D_V3_WALK2;
+    const VT* const C = WALK ? reinterpret_cast<const VT*>(Cv) : reinterpret_cast<const VT*>(Cv) + (size_t)frame * H * W1 * 32 + lane;
+    VT* const S = WALK ? reinterpret_cast<VT*>(Sv) : reinterpret_cast<VT*>(Sv) + (size_t)frame * H * W1 * 32 + lane;
+    const ptrdiff_t rstride = (ptrdiff_t)sy * W1 * 32;                       // elements from a row to the next one of the sweep
+    size_t off = (((size_t)frame * H + (sy > 0 ? 0 : H - 1)) * W1 + gcol0) * 32 + lane;   // WALK: this warp's first column in the current row
 
     uint32_t zr[NR];
 #pragma unroll
@@ -176,7 +187,7 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
     VT cq[CPW];
     {
         const int y = sy > 0 ? 0 : H - 1;
-        const VT* Crow = C + ((size_t)y * W1 + gcol0) * 32;
+        const VT* Crow = WALK ? C + off : C + ((size_t)y * W1 + gcol0) * 32;
 #pragma unroll
         for (int j = 0; j < CPW; j++)
             if (j < nv) cq[j] = ld_c<NR>(Crow + j * 32);
@@ -257,14 +268,14 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         const int yn = sy > 0 ? i + 1 : H - 2 - i;
         const int par = i & 1;
         const bool more = i + 1 < H;
-        const VT* Cnext = C + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
-        VT* Srow = S + ((size_t)y * W1 + gcol0) * 32;
-        const VT* Snext = S + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
+        const size_t off_next = more ? off + rstride : off;
+        const VT* Cnext = WALK ? C + off_next : C + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
+        VT* Srow = WALK ? S + off : S + ((size_t)y * W1 + gcol0) * 32;
+        const VT* Snext = WALK ? S + off_next : S + ((size_t)(more ? yn : y) * W1 + gcol0) * 32;
 #if V3D_V3_D256_HINTS
         if constexpr (NR == 4) {
             // row i + 2 (clamped to the last row: a redundant prefetch is cheaper than a branch)
-            const int y2 = sy > 0 ? min(i + 2, H - 1) : max(H - 3 - i, 0);
-            const VT* C2 = C + ((size_t)y2 * W1 + gcol0) * 32;
+            const VT* C2 = C + (i + 2 < H ? off + 2 * rstride : off_next);
 #pragma unroll
             for (int j = 0; j < CPW; j++)
                 if (j < nv) prefetch_l2(C2 + j * 32);
@@ -376,6 +387,7 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
                 }
             }
         }
+        if constexpr (WALK) off = off_next;
     }
     (void)zeros;
     cluster.sync();   // nobody may exit while a neighbour can still read its shared memory
