@@ -288,6 +288,8 @@ k_path_vert3(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, int W1,
         uint4 nb;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(nb.x), "=r"(nb.y), "=r"(nb.z), "=r"(nb.w) : "r"(nbr_addr));
         const uint32_t par_off = lane_off + par * PARSTRIDE * (uint32_t)sizeof(VT);
+        V3D_DASSERT(!has_left || (nb.x + lane_off == to_l && nb.y == to_l_bar));      // the table holds this lane's own mapa results
+        V3D_DASSERT(!has_right || (nb.z + lane_off == to_r && nb.w == to_r_bar));
         if (has_right) st_async(nb.z + par_off, Ml[((NR <= 2 && CPW >= 4 ? nv : CPW) - 1) * 32], nb.w + par * V3_NW * 8);
         if (has_left) st_async(nb.x + par_off, Mr[0], nb.y + par * V3_NW * 8);
         if (lane == 0 && rx_bytes) mbar_expect_tx(my_bar + par * V3_NW, rx_bytes);
