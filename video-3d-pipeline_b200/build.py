@@ -18,7 +18,7 @@ CSRC = HERE / "csrc"
 OBJ = HERE / "build"
 OUT = Path(os.environ.get("V3D_LIB_OUT") or (HERE / "video_3d_pipeline" / "libv3d.so"))   # V3D_LIB_OUT: build a variant elsewhere
 SOURCES = ["v3d_api.cu", "k_gray.cu", "k_cost.cu", "k_paths.cu", "k_paths_h.cu", "k_post.cu", "k_guided.cu", "k_png.cu",
-           "k_probe.cu", "k_nvdec.cu"]
+           "k_probe.cu"]
 HEADERS = [CSRC / "v3d_internal.h", CSRC / "path_common.cuh", CSRC / "tma.cuh", HERE.parent / "include" / "v3d.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

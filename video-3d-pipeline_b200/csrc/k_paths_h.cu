@@ -73,6 +73,14 @@ k_path_lr_ckpt(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ ckpt, int
     uint32_t M[NR];
 #pragma unroll
     for (int r = 0; r < NR; r++) M[r] = 0;
+#if V3D_STEP_CARRY
+    uint32_t mm = 0;                                 // M holds L, mm its minimum over d (path_step_carry)
+    auto step = [&](const uint32_t (&Cr)[NR]) { path_step_carry<NR>(M, mm, Cr, P1p, P2p, lane); };
+    auto checkpoint = [&](VT* dst) { uint32_t Ms[NR]; carry_to_state<NR>(M, mm, P2p, Ms); *dst = pack<NR>(Ms); };
+#else
+    auto step = [&](const uint32_t (&Cr)[NR]) { uint32_t L[NR]; path_step<NR>(M, Cr, L, P1p, P2p, lane); };
+    auto checkpoint = [&](VT* dst) { *dst = pack<NR>(M); };
+#endif
     for (int c = 0; c < nchunks; c++) {
         const int st = c % NST;
         mbar_wait(&bars[wib][st], (uint32_t)((c / NST) & 1));
@@ -85,17 +93,17 @@ k_path_lr_ckpt(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ ckpt, int
         if (n == CH) {
 #pragma unroll
             for (int j = 0; j < CH; j++) {
-                if (take && j == jstar) ck[(size_t)cr * 32] = pack<NR>(M);
-                uint32_t Cr[NR], L[NR];
+                if (take && j == jstar) checkpoint(&ck[(size_t)cr * 32]);
+                uint32_t Cr[NR];
                 unpack<NR>(cs[j * 32], Cr);
-                path_step<NR>(M, Cr, L, P1p, P2p, lane);
+                step(Cr);
             }
         } else {
             for (int j = 0; j < n; j++) {
-                if (take && j == jstar) ck[(size_t)cr * 32] = pack<NR>(M);
-                uint32_t Cr[NR], L[NR];
+                if (take && j == jstar) checkpoint(&ck[(size_t)cr * 32]);
+                uint32_t Cr[NR];
                 unpack<NR>(cs[j * 32], Cr);
-                path_step<NR>(M, Cr, L, P1p, P2p, lane);
+                step(Cr);
             }
         }
         __syncwarp();                                // every lane is done reading this stage
@@ -174,6 +182,17 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
     uint32_t M[NR];
 #pragma unroll
     for (int r = 0; r < NR; r++) M[r] = 0;
+#if V3D_STEP_CARRY
+    uint32_t mmr = 0, mml = 0;                       // M / Ml hold L of the last pixel, mmr / mml its minimum over d
+    // one step of a direction: state in, this pixel's L out
+    auto step_r = [&](const uint32_t (&Cr)[NR], uint32_t (&L)[NR]) {
+        path_step_carry<NR>(M, mmr, Cr, P1p, P2p, lane);
+#pragma unroll
+        for (int r = 0; r < NR; r++) L[r] = M[r];
+    };
+#else
+    auto step_r = [&](const uint32_t (&Cr)[NR], uint32_t (&L)[NR]) { path_step<NR>(M, Cr, L, P1p, P2p, lane); };
+#endif
     for (int c = 0; c < nchunks; c++) {
         const int st = c % NST;
         mbar_wait(&bars[wib][st], (uint32_t)((c / NST) & 1));
@@ -187,6 +206,16 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
 #pragma unroll
             for (int r = 0; r < NR; r++) Ml[r] = 0;
         }
+#if V3D_STEP_CARRY
+        mml = 0;                                     // a checkpoint is M: (L = M, min = 0)
+        auto step_l = [&](const uint32_t (&Cr)[NR], uint32_t (&L)[NR]) {
+            path_step_carry<NR>(Ml, mml, Cr, P1p, P2p, lane);
+#pragma unroll
+            for (int r = 0; r < NR; r++) L[r] = Ml[r];
+        };
+#else
+        auto step_l = [&](const uint32_t (&Cr)[NR], uint32_t (&L)[NR]) { path_step<NR>(Ml, Cr, L, P1p, P2p, lane); };
+#endif
         if (n == CH) {
             // Steps 0..3 keep their two L in registers; steps 4..7 meet the pixels the other direction has already
             // visited, so every pixel's S is read and written ONCE (S + L_left-to-right + L_right-to-left).
@@ -197,8 +226,8 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
                 uint32_t Ca[NR], Cb[NR], Sa[NR], Sb[NR], La[NR], Lb[NR];
                 unpack<NR>(cs[i * 32], Ca);
                 unpack<NR>(cs[j * 32], Cb);
-                path_step<NR>(Ml, Ca, La, P1p, P2p, lane);       // left to right at pixel i
-                path_step<NR>(M, Cb, Lb, P1p, P2p, lane);        // right to left at pixel 7 - i
+                step_l(Ca, La);                                  // left to right at pixel i
+                step_r(Cb, Lb);                                  // right to left at pixel 7 - i
                 if (i < CH / 2) {
 #pragma unroll
                     for (int r = 0; r < NR; r++) { keepA[i][r] = La[r]; keepB[i][r] = Lb[r]; }
@@ -218,7 +247,7 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
                 uint32_t Cr[NR], Sr[NR], L[NR];
                 unpack<NR>(cs[j * 32], Cr);
                 unpack<NR>(ss[j * 32], Sr);
-                path_step<NR>(Ml, Cr, L, P1p, P2p, lane);
+                step_l(Cr, L);
 #pragma unroll
                 for (int r = 0; r < NR; r++) Sr[r] += L[r];
                 ss[j * 32] = pack<NR>(Sr);
@@ -227,7 +256,7 @@ k_path_rl_wta_tma(const uint16_t* __restrict__ Cv, uint16_t* __restrict__ Sv, co
                 uint32_t Cr[NR], Sr[NR], L[NR];
                 unpack<NR>(cs[j * 32], Cr);
                 unpack<NR>(ss[j * 32], Sr);
-                path_step<NR>(M, Cr, L, P1p, P2p, lane);
+                step_r(Cr, L);
 #pragma unroll
                 for (int r = 0; r < NR; r++) Sr[r] += L[r];
                 ss[j * 32] = pack<NR>(Sr);
