@@ -326,7 +326,7 @@ def run_ours(args):
                 Bl = probe.fused_sweep_clusters or 15
             per_frame = probe.workspace_bytes
         # lanes that fit: workspace + guided coefficients + device-resident and staged copies of the inputs / outputs
-        per_frame += (16 * GW * GH if cfg.upscale else 0) + 2 * (cfg.h2d + cfg.d2h)
+        per_frame += (16 * GW * GH if cfg.upscale else 0) + 3 * (cfg.h2d + cfg.d2h)
         free_b, _total_b = torch.cuda.mem_get_info(dev)
         n_lanes = max(1, min(n_lanes, int((free_b - 8e9) // (Bl * per_frame))))
         if world > 1:   # every rank must do the same amount of work (weak scaling): agree on the minimum
@@ -351,10 +351,12 @@ def run_ours(args):
                     t = torch.from_numpy(a[i:i + Bl])
                 self.h[k] = t.pin_memory()
                 self.d[k] = self.h[k].to(dev)
+            # two host output buffers per lane: a context keeps two host calls in flight (submit k+1, wait for k)
             if cfg.upscale:
-                self.out_h = torch.empty((Bl, GH, GW), dtype=torch.uint16).pin_memory()
+                self.out_hs = [torch.empty((Bl, GH, GW), dtype=torch.uint16).pin_memory() for _ in range(2)]
                 self.out_d = torch.empty((Bl, GH, GW), dtype=torch.uint16, device=dev)
-            self.disp_h = torch.empty((Bl, H, W), dtype=torch.int16).pin_memory() if cfg.depth else None
+            self.disp_hs = [torch.empty((Bl, H, W), dtype=torch.int16).pin_memory() for _ in range(2)] if cfg.depth else None
+            self.calls = 0
 
         # device-resident step
         def step_device(self, depth_only=False):
@@ -368,6 +370,11 @@ def run_ours(args):
 
         # end-to-end step through the host entry point: submit now, wait later
         def submit_host(self, depth_only=False, copy_only=False):
+            if self.ctx.host_pending >= args.inflight:
+                self.ctx.host_wait_oldest()
+            self.out_h = self.out_hs[self.calls & 1] if cfg.upscale else None
+            self.disp_h = self.disp_hs[self.calls & 1] if cfg.depth else None
+            self.calls += 1
             with torch.cuda.stream(self.stream):
                 if copy_only:
                     out = {"out4k": self.out_h} if cfg.upscale else {"disp": self.disp_h}
@@ -394,7 +401,8 @@ def run_ours(args):
         """K steps of every lane between two events on the current stream; lanes fork from / join into it.
         Everything is submitted by THIS thread: the device-resident calls are asynchronous launches, the host calls
         are v3d_*_host_async submissions and the thread only ever sleeps in v3d_host_wait (blocking-sync event) on
-        the lane it is about to resubmit, while the other lanes' work is already queued."""
+        the lane it is about to resubmit (each lane keeps two calls in flight: the uploads of call k+1 run under the
+        kernels of call k), while the other lanes' work is already queued."""
         def all_lanes(n):
             if kind == "device":
                 for _ in range(n):
@@ -403,8 +411,7 @@ def run_ours(args):
             else:
                 for _ in range(n):
                     for lane in lanes:
-                        lane.wait_host()
-                        lane.submit_host(**kw)
+                        lane.submit_host(**kw)       # sleeps for the lane's oldest call when two are in flight
                 for lane in lanes:
                     lane.wait_host()
 
@@ -539,7 +546,7 @@ def run_ours(args):
                     "host_copy_ceiling": copy_ceiling, "frac_of_host_copy_ceiling": e2e / copy_ceiling,
                     "host_gbs": {"h2d": world * B * cfg.h2d * args.steps / (ms_e2e / 1000.0) / 1e9,
                                  "d2h": world * B * cfg.d2h * args.steps / (ms_e2e / 1000.0) / 1e9},
-                    "submit": "one host thread per rank; v3d_*_host_async + v3d_host_wait (blocking-sync event), "
+                    "submit": "one host thread per rank, two calls in flight per lane; v3d_*_host_async + v3d_host_wait_oldest (blocking-sync event), "
                               "per-frame copies on separate upload / download streams"},
             "gpu_launches": launches,
             "roofline": roofline,
@@ -571,6 +578,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0,
                     help="frames per step per GPU (default: lanes x the co-resident clusters of the fused sweep, 90 on most B200s)")
     ap.add_argument("--lanes", type=int, default=6, help="streams/contexts the batch is split over")
+    ap.add_argument("--inflight", type=int, default=2, choices=[1, 2],
+                    help="end-to-end host calls in flight per lane (2: uploads of call k+1 under the kernels of call k)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-depth-only", action="store_true")

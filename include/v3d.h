@@ -165,9 +165,14 @@ int v3d_depth_frames_host(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, 
  * caller that keeps several batches in flight): enqueues the uploads -- one copy per frame on the
  * context's upload stream, SBS frames first so that the SGBM chain runs under the guide upload -- the
  * kernels on `stream`, and the downloads (one copy per frame, on the context's download stream), then
- * returns without waiting.  `stream` finally waits for the downloads, so the call is stream-ordered as a
- * whole.  The host buffers must stay valid, and the context must not be used by another host call, until
- * v3d_host_wait(ctx) has returned.  v3d_depth_frames_host = this + v3d_host_wait. */
+ * returns without waiting.
+ * TWO calls may be in flight per context (each has its own staging buffers): the uploads of call k+1 run
+ * under the kernels of call k, the 4K download of call k under the kernels of call k+1.  A third call
+ * first waits (sleeping) for the oldest one.  The uploads start at once: the host input buffers must be
+ * complete when the call is made.  `stream` waits for the kernels and for the downloads of disp /
+ * depth_f32 / depth_u16; the download of out_4k completes on its own -- the host buffers of a call must
+ * stay valid, and its outputs must not be read, until v3d_host_wait_oldest / v3d_host_wait has covered
+ * it.  v3d_depth_frames_host = this + v3d_host_wait. */
 int v3d_depth_frames_host_async(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, int h, int batch,
                                 int unsqueeze, int16_t* disp_host, float* depth_f32_host,
                                 uint16_t* depth_u16_host, const uint8_t* guide_rgb_host, int gw, int gh,
@@ -178,10 +183,14 @@ int v3d_depth_frames_host_async(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int s
 int v3d_guided_upscale_host_async(v3d_ctx* ctx, const uint16_t* depth_u16_host, const uint8_t* guide_rgb_host,
                                   int gw, int gh, int batch, int r, float eps, uint16_t* out_u16_host,
                                   void* stream);
-/* Block the calling host thread until the context's last *_host_async call has delivered its outputs.
+/* Block the calling host thread until EVERY *_host_async call of the context has delivered its outputs.
  * The wait sleeps on a blocking-sync CUDA event (no spinning), so one submit thread can drive many
  * contexts and many ranks can share few host cores. */
 int v3d_host_wait(v3d_ctx* ctx);
+/* The same for the OLDEST call in flight only (the pipelined loop: submit k+1, wait for k); no-op when
+ * nothing is pending.  v3d_host_pending: calls in flight (0, 1 or 2). */
+int v3d_host_wait_oldest(v3d_ctx* ctx);
+int v3d_host_pending(const v3d_ctx* ctx);
 /* Measurement aid: exactly the host<->device copies of v3d_depth_frames_host_async (same streams, same
  * per-frame granularity, same event dependencies) with NO kernel in between -- the ceiling the host side
  * of a box puts on the end-to-end number.  disp_host / out_4k_host receive whatever the workspace holds. */

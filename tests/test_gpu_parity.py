@@ -438,6 +438,62 @@ def test_async_host_calls_from_one_submit_thread():
             c.close()
 
 
+def test_two_host_calls_in_flight_per_context():
+    """A context keeps TWO asynchronous host calls in flight (own staging buffers per call): submit k+1, then wait for
+    k.  Every call's outputs equal the synchronous device path on that call's inputs, whatever the order of
+    submissions, waits and implicit waits (a third submission first waits for the oldest call)."""
+    W, H, D, B, N = 320, 96, 64, 3, 5
+    frames = [np.stack([synthetic.sbs_frame(70 + k, t, W, H, D) for t in range(B)]) for k in range(N)]
+    guides = [np.stack([synthetic.guide_frame(70 + k, t, 2 * W, 2 * H) for t in range(B)]) for k in range(N)]
+    fh = [torch.from_numpy(f).pin_memory() for f in frames]
+    gh = [torch.from_numpy(g).pin_memory() for g in guides]
+    outs = [dict(disp=torch.full((B, H, W), -7, dtype=torch.int16).pin_memory(),
+                 u16=torch.zeros((B, H, W), dtype=torch.uint16).pin_memory(),
+                 out4k=torch.zeros((B, 2 * H, 2 * W), dtype=torch.uint16).pin_memory()) for _ in range(N)]
+    ctx = nv.Context(W, H, nv.SgbmParams(numDisparities=D), max_batch=B)
+    stream = torch.cuda.Stream()
+    try:
+        assert ctx.host_pending == 0
+        with torch.cuda.stream(stream):
+            for k in range(N):
+                if k % 2:                                    # alternate: with and without the upscale step
+                    ctx.depth_frames_host(fh[k], False, gh[k], 8, 1e-3, out=outs[k], wait=False)
+                else:
+                    ctx.depth_frames_host(fh[k], False, out={"disp": outs[k]["disp"], "u16": outs[k]["u16"]}, wait=False)
+                assert ctx.host_pending == min(k + 1, 2)     # the third submission waited for the oldest call
+                if k == 1:
+                    ctx.host_wait_oldest()                   # explicit: call 0 is complete, call 1 still in flight
+                    assert ctx.host_pending == 1
+        ctx.host_wait()
+        assert ctx.host_pending == 0
+        ctx.host_wait_oldest()                               # nothing pending: no-op
+        for k in range(N):
+            want = ("disp", "u16")
+            if k % 2:
+                ref = ctx.depth_frames(torch.from_numpy(frames[k]).cuda(), False, torch.from_numpy(guides[k]).cuda(), 8, 1e-3, want=want)
+            else:
+                ref = ctx.depth_frames(torch.from_numpy(frames[k]).cuda(), False, want=want)
+            torch.cuda.synchronize()
+            assert torch.equal(ref["disp"].cpu(), outs[k]["disp"]), k
+            assert torch.equal(ref["u16"].cpu().view(torch.int16), outs[k]["u16"].view(torch.int16)), k
+            if k % 2:
+                assert torch.equal(ref["out4k"].cpu().view(torch.int16), outs[k]["out4k"].view(torch.int16)), k
+        # upscale-only calls share one workspace buffer for the uploaded depth maps: still exact back to back
+        d = [np.stack([synthetic.depth_u16(9 + k, t, W, H) for t in range(B)]) for k in range(3)]
+        dh = [torch.from_numpy(x.view(np.int16)).view(torch.uint16).pin_memory() for x in d]
+        o = [torch.zeros((B, 2 * H, 2 * W), dtype=torch.uint16).pin_memory() for _ in range(3)]
+        with torch.cuda.stream(stream):
+            for k in range(3):
+                ctx.guided_upscale_host(dh[k], gh[k], o[k], 8, 1e-3, wait=False)
+        ctx.host_wait()
+        for k in range(3):
+            want = ctx.guided_upscale(dh[k].cuda(), gh[k].cuda(), 8, 1e-3)
+            torch.cuda.synchronize()
+            assert torch.equal(want.cpu().view(torch.int16), o[k].view(torch.int16)), k
+    finally:
+        ctx.close()
+
+
 def test_row_checkpoints_cover_every_width_remainder():
     """The left-to-right direction is re-run from a checkpoint per 8-pixel chunk, chunks counted from the right
     end of the row: every W1 % 8 (and rows shorter than one chunk) must give cv2's disparities, S taps included."""

@@ -24,6 +24,9 @@ constexpr int GRMAX = 16;   // largest supported radius (8 and 4 have compile-ti
 #ifndef V3D_GUIDED_DEPTH_PREFETCH
 #define V3D_GUIDED_DEPTH_PREFETCH 0
 #endif
+#ifndef V3D_GUIDED_APPLY_HOIST
+#define V3D_GUIDED_APPLY_HOIST 1
+#endif
 
 __device__ __forceinline__ int reflect_idx(int i, int n)
 {
@@ -450,8 +453,25 @@ k_guided_apply_s(const float4* __restrict__ ab, const uint8_t* __restrict__ guid
     const float inv_n = 1.0f / (float)(win * win), k255 = 1.0f / 255.0f;
     const int wslot = tid + tid / GR;
     int nslot = 0, oslot = R;            // slot of the entering row j and of the leaving row j - win (= j + R mod RING)
+    // Horizontal pass: item = (row of the group, run of GR output columns); R * runs <= TW < NT, so a thread owns at most
+    // one item per group, the same (row, run) in every group.
+    static_assert(R <= GR, "one horizontal item per thread and group");
+    const int h_jj = tid / runs, h_run = tid - h_jj * runs, h_xb = h_run * GR;
+    const bool h_mine = tid < R * runs && X0 + h_xb < gw;
 
     for (int g = 0; g * R < nrows; g++) {
+#if V3D_GUIDED_APPLY_HOIST
+        // the item's 24 guide bytes are requested HERE, a whole vertical pass and a block barrier ahead of their use
+        // (they were 36 % of this kernel's stall samples when requested next to the window sums)
+        uint2 u0 = make_uint2(0u, 0u), u1 = u0, u2 = u0;
+        {
+            const int o = g * R + h_jj - 2 * r;
+            if (VEC && h_mine && o >= 0 && o < seg_h) {
+                const uint2* gp = reinterpret_cast<const uint2*>(guide + ((size_t)(Y0 + o) * gw + X0 + h_xb) * 3);
+                u0 = __ldg(gp); u1 = __ldg(gp + 1); u2 = __ldg(gp + 2);
+            }
+        }
+#endif
         asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
         for (int jj = 0; jj < R; jj++) {
@@ -469,21 +489,22 @@ k_guided_apply_s(const float4* __restrict__ ab, const uint8_t* __restrict__ guid
         __syncthreads();
         fetch_rows(g + 1);               // lands while the horizontal pass runs
 
-        for (int it = tid; it < R * runs; it += NT) {
-            const int jj = it / runs, run = it - jj * runs;
-            const int o = g * R + jj - 2 * r;
-            const int xb = run * GR, X = X0 + xb;
-            if (o < 0 || o >= seg_h || X >= gw) continue;
+        const int o = g * R + h_jj - 2 * r;
+        if (h_mine && o >= 0 && o < seg_h) {
+            const int jj = h_jj, run = h_run;
+            const int xb = h_xb, X = X0 + xb;
             const int Y = Y0 + o;
             const float4* vr = vbuf + jj * VP + xb + run;          // window start; xb is a multiple of GR
             auto at = [&](int dx) -> float4 { return vr[RT > 0 ? dx + dx / GR : (xb + dx) + (xb + dx) / GR - xb - run]; };
             const size_t base = (size_t)Y * gw + X;
+#if !V3D_GUIDED_APPLY_HOIST
             // the run's 24 guide bytes are requested before the window sums so that their latency hides behind them
             uint2 u0 = make_uint2(0u, 0u), u1 = u0, u2 = u0;
             if (VEC) {
                 const uint2* gp = reinterpret_cast<const uint2*>(guide + base * 3);
                 u0 = __ldg(gp); u1 = __ldg(gp + 1); u2 = __ldg(gp + 2);
             }
+#endif
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (RT > 0) {
 #pragma unroll

@@ -82,7 +82,8 @@ void v3d_default_params(v3d_sgbm_params* p)
 static void free_all(v3d_ctx* c)
 {
     void* ptrs[] = { c->grayL, c->grayR, c->rexp, c->lexp, c->C, c->S, c->ckpt, c->rec, c->raw, c->med, c->disp, c->labels,
-                     c->sizes, c->minmax, c->png_sums, c->f32_tmp, c->u16_tmp, c->ab, c->in_dev, c->guide_dev, c->out_dev };
+                     c->sizes, c->minmax, c->png_sums, c->f32_tmp, c->u16_tmp, c->ab, c->hs[0].in_dev, c->hs[0].guide_dev,
+                     c->hs[0].out_dev, c->hs[1].in_dev, c->hs[1].guide_dev, c->hs[1].out_dev };
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -196,7 +197,8 @@ int v3d_destroy(v3d_ctx* ctx)
     if (ctx->side_stream) { cudaStreamDestroy(ctx->side_stream); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
     if (ctx->up_stream) {
         cudaStreamDestroy(ctx->up_stream); cudaStreamDestroy(ctx->down_stream);
-        cudaEvent_t evs[] = { ctx->ev_entry, ctx->ev_sbs, ctx->ev_guide, ctx->ev_compute, ctx->ev_done };
+        cudaEvent_t evs[] = { ctx->ev_entry, ctx->ev_small, ctx->hs[0].ev_sbs, ctx->hs[0].ev_guide, ctx->hs[0].ev_compute,
+                              ctx->hs[0].ev_done, ctx->hs[1].ev_sbs, ctx->hs[1].ev_guide, ctx->hs[1].ev_compute, ctx->hs[1].ev_done };
         for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     }
     free_all(ctx);
@@ -445,17 +447,32 @@ int host_streams(v3d_ctx* ctx)
     if (ctx->up_stream) return V3D_OK;
     V3D_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
     V3D_CUDA(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
-    cudaEvent_t* evs[] = { &ctx->ev_entry, &ctx->ev_sbs, &ctx->ev_guide, &ctx->ev_compute };
+    cudaEvent_t* evs[] = { &ctx->ev_entry, &ctx->ev_small, &ctx->hs[0].ev_sbs, &ctx->hs[0].ev_guide, &ctx->hs[0].ev_compute,
+                           &ctx->hs[1].ev_sbs, &ctx->hs[1].ev_guide, &ctx->hs[1].ev_compute };
     for (cudaEvent_t* e : evs) V3D_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    // the host waits on this one: blocking sync = the thread sleeps on an OS primitive instead of spinning, so
+    // the host waits on these: blocking sync = the thread sleeps on an OS primitive instead of spinning, so
     // many lanes and ranks can share few host cores
-    V3D_CUDA(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
+    for (auto& sl : ctx->hs) V3D_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
+    return V3D_OK;
+}
+
+// wait (sleeping) for the call that occupies a slot
+int slot_wait(v3d_ctx* ctx, int s)
+{
+    auto& sl = ctx->hs[s];
+    if (!sl.pending) return V3D_OK;
+    sl.pending = 0;
+    V3D_CUDA(cudaEventSynchronize(sl.ev_done));
     return V3D_OK;
 }
 
 // Enqueue one host call.  Three streams: uploads (frame by frame, SBS first: the SGBM chain starts as soon as the
 // SBS frames are in and runs under the guide upload), kernels on the caller's stream, downloads (frame by frame).
-// The caller's stream finally waits for the downloads, so the call stays stream-ordered as a whole.
+// Two calls may be in flight; call k uses slot k & 1 (its own staging buffers and events), so
+//   * the uploads of call k+1 only wait for the kernels of call k-1 (the previous readers of the slot's buffers) and
+//     run under the kernels of call k;
+//   * the caller's stream waits for the downloads of disp / depth_f32 / depth_u16 (they read workspace buffers the
+//     next call's kernels overwrite) but not for the 4K download, which runs under the next call's kernels.
 int host_submit(v3d_ctx* ctx, const HostJob& j, cudaStream_t st)
 {
     int rc;
@@ -464,57 +481,67 @@ int host_submit(v3d_ctx* ctx, const HostJob& j, cudaStream_t st)
     const size_t sbs_frame = (size_t)j.sbs_w * j.h * 3;
     const size_t guide_frame = (size_t)j.gw * j.gh * 3, out_frame = (size_t)j.gw * j.gh * 2;
     if ((rc = host_streams(ctx))) return rc;
-    if (j.sbs && (rc = ensure(ctx, (void**)&ctx->in_dev, &ctx->in_bytes, sbs_frame * B))) return rc;
+    const int s = (int)(ctx->host_calls & 1);
+    auto& sl = ctx->hs[s];
+    if ((rc = slot_wait(ctx, s))) return rc;       // a third call in flight first waits for the oldest one
+    if (j.sbs && (rc = ensure(ctx, (void**)&sl.in_dev, &sl.in_bytes, sbs_frame * B))) return rc;
     if (j.guide) {
-        if ((rc = ensure(ctx, (void**)&ctx->guide_dev, &ctx->guide_bytes, guide_frame * B))) return rc;
-        if ((rc = ensure(ctx, (void**)&ctx->out_dev, &ctx->out_bytes, out_frame * B))) return rc;
+        if ((rc = ensure(ctx, (void**)&sl.guide_dev, &sl.guide_bytes, guide_frame * B))) return rc;
+        if ((rc = ensure(ctx, (void**)&sl.out_dev, &sl.out_bytes, out_frame * B))) return rc;
     }
     cudaStream_t up = ctx->up_stream, down = ctx->down_stream;
-    V3D_CUDA(cudaEventRecord(ctx->ev_entry, st));
-    V3D_CUDA(cudaStreamWaitEvent(up, ctx->ev_entry, 0));
+    if (sl.used) V3D_CUDA(cudaStreamWaitEvent(up, sl.ev_compute, 0));     // the slot's staged inputs have been consumed
+    if (j.depth_in) {
+        // the depth maps go straight into a workspace buffer that earlier work on the caller's stream may still read
+        V3D_CUDA(cudaEventRecord(ctx->ev_entry, st));
+        V3D_CUDA(cudaStreamWaitEvent(up, ctx->ev_entry, 0));
+    }
     {
         V3dScope scope(ctx, ST_COPY, up);
         if (j.sbs)
             for (int f = 0; f < B; f++)
-                V3D_CUDA(cudaMemcpyAsync(ctx->in_dev + f * sbs_frame, j.sbs + f * sbs_frame, sbs_frame, cudaMemcpyHostToDevice, up));
+                V3D_CUDA(cudaMemcpyAsync(sl.in_dev + f * sbs_frame, j.sbs + f * sbs_frame, sbs_frame, cudaMemcpyHostToDevice, up));
         if (j.depth_in)
             V3D_CUDA(cudaMemcpyAsync(ctx->u16_tmp, j.depth_in, npx * 2 * B, cudaMemcpyHostToDevice, up));
-        V3D_CUDA(cudaEventRecord(ctx->ev_sbs, up));
+        V3D_CUDA(cudaEventRecord(sl.ev_sbs, up));
         if (j.guide) {
             for (int f = 0; f < B; f++)
-                V3D_CUDA(cudaMemcpyAsync(ctx->guide_dev + f * guide_frame, j.guide + f * guide_frame, guide_frame, cudaMemcpyHostToDevice, up));
-            V3D_CUDA(cudaEventRecord(ctx->ev_guide, up));
+                V3D_CUDA(cudaMemcpyAsync(sl.guide_dev + f * guide_frame, j.guide + f * guide_frame, guide_frame, cudaMemcpyHostToDevice, up));
+            V3D_CUDA(cudaEventRecord(sl.ev_guide, up));
         }
     }
-    V3D_CUDA(cudaStreamWaitEvent(st, ctx->ev_sbs, 0));
+    V3D_CUDA(cudaStreamWaitEvent(st, sl.ev_sbs, 0));
     if (j.sbs && !j.copy_only) {
-        rc = v3d_depth_frames(ctx, ctx->in_dev, (size_t)j.sbs_w * 3, sbs_frame, j.sbs_w, j.h, B, j.unsqueeze, ctx->disp,
+        rc = v3d_depth_frames(ctx, sl.in_dev, (size_t)j.sbs_w * 3, sbs_frame, j.sbs_w, j.h, B, j.unsqueeze, ctx->disp,
                               j.f32 ? ctx->f32_tmp : nullptr, j.u16 || j.guide ? ctx->u16_tmp : nullptr,
                               nullptr, 0, 0, j.r, j.eps, nullptr, st);
         if (rc) return rc;
     }
     if (j.guide) {
-        V3D_CUDA(cudaStreamWaitEvent(st, ctx->ev_guide, 0));
+        V3D_CUDA(cudaStreamWaitEvent(st, sl.ev_guide, 0));
+        if (sl.used) V3D_CUDA(cudaStreamWaitEvent(st, sl.ev_done, 0));    // the slot's previous output has left the device
         if (!j.copy_only)
-            if ((rc = v3d_guided_upscale(ctx, ctx->u16_tmp, ctx->W, ctx->H, ctx->guide_dev, j.gw, j.gh, B, j.r, j.eps,
-                                         ctx->out_dev, nullptr, st))) return rc;
+            if ((rc = v3d_guided_upscale(ctx, ctx->u16_tmp, ctx->W, ctx->H, sl.guide_dev, j.gw, j.gh, B, j.r, j.eps,
+                                         sl.out_dev, nullptr, st))) return rc;
     }
-    V3D_CUDA(cudaEventRecord(ctx->ev_compute, st));
-    V3D_CUDA(cudaStreamWaitEvent(down, ctx->ev_compute, 0));
+    V3D_CUDA(cudaEventRecord(sl.ev_compute, st));
+    V3D_CUDA(cudaStreamWaitEvent(down, sl.ev_compute, 0));
     {
         V3dScope scope(ctx, ST_COPY, down);
         if (j.disp) V3D_CUDA(cudaMemcpyAsync(j.disp, ctx->disp, npx * 2 * B, cudaMemcpyDeviceToHost, down));
         if (j.f32) V3D_CUDA(cudaMemcpyAsync(j.f32, ctx->f32_tmp, npx * 4 * B, cudaMemcpyDeviceToHost, down));
         if (j.u16) V3D_CUDA(cudaMemcpyAsync(j.u16, ctx->u16_tmp, npx * 2 * B, cudaMemcpyDeviceToHost, down));
+        V3D_CUDA(cudaEventRecord(ctx->ev_small, down));
         if (j.out4k)
             for (int f = 0; f < B; f++)
-                V3D_CUDA(cudaMemcpyAsync(j.out4k + f * (out_frame / 2), ctx->out_dev + f * (out_frame / 2), out_frame,
+                V3D_CUDA(cudaMemcpyAsync(j.out4k + f * (out_frame / 2), sl.out_dev + f * (out_frame / 2), out_frame,
                                          cudaMemcpyDeviceToHost, down));
     }
-    V3D_CUDA(cudaEventRecord(ctx->ev_done, down));
-    V3D_CUDA(cudaStreamWaitEvent(st, ctx->ev_done, 0));
-    ctx->host_pending = 1;
-    ctx->host_calls++;
+    V3D_CUDA(cudaEventRecord(sl.ev_done, down));
+    V3D_CUDA(cudaStreamWaitEvent(st, ctx->ev_small, 0));
+    sl.pending = 1;
+    sl.used = 1;
+    sl.call = ctx->host_calls++;
     return V3D_OK;
 }
 
@@ -580,12 +607,24 @@ int v3d_host_copy_only_async(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_
 int v3d_host_wait(v3d_ctx* ctx)
 {
     if (!ctx) return v3d_fail(V3D_EINVAL, "null context");
-    if (!ctx->host_pending) return V3D_OK;
+    if (!ctx->hs[0].pending && !ctx->hs[1].pending) return V3D_OK;
     V3D_CUDA(cudaSetDevice(ctx->device));
-    ctx->host_pending = 0;
-    V3D_CUDA(cudaEventSynchronize(ctx->ev_done));
-    return V3D_OK;
+    const int first = (ctx->hs[0].pending && ctx->hs[1].pending && ctx->hs[1].call < ctx->hs[0].call) ? 1 : 0;
+    if (int rc = slot_wait(ctx, first)) return rc;
+    return slot_wait(ctx, first ^ 1);
 }
+
+int v3d_host_wait_oldest(v3d_ctx* ctx)
+{
+    if (!ctx) return v3d_fail(V3D_EINVAL, "null context");
+    const bool p0 = ctx->hs[0].pending != 0, p1 = ctx->hs[1].pending != 0;
+    if (!p0 && !p1) return V3D_OK;
+    V3D_CUDA(cudaSetDevice(ctx->device));
+    const int s = (p0 && p1) ? (ctx->hs[1].call < ctx->hs[0].call ? 1 : 0) : (p0 ? 0 : 1);
+    return slot_wait(ctx, s);
+}
+
+int v3d_host_pending(const v3d_ctx* ctx) { return ctx ? (ctx->hs[0].pending != 0) + (ctx->hs[1].pending != 0) : 0; }
 
 int v3d_depth_frames_host(v3d_ctx* ctx, const uint8_t* sbs_bgr_host, int sbs_w, int h, int batch, int unsqueeze,
                           int16_t* disp_host, float* depth_f32_host, uint16_t* depth_u16_host,

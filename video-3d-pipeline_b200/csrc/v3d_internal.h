@@ -51,16 +51,23 @@ struct v3d_ctx {
     uint16_t* u16_tmp;           // [B][H][W]
     // lazily sized buffers
     float4* ab; size_t ab_bytes;           // guided coefficients [B][gh][gw]
-    uint8_t* in_dev; size_t in_bytes;      // host-API staging: SBS frames
-    uint8_t* guide_dev; size_t guide_bytes;
-    uint16_t* out_dev; size_t out_bytes;
     // host entry points (v3d_depth_frames_host_async): uploads and downloads run frame by frame on their own streams
     // so that both DMA engines stay busy next to the kernels; completion is a blocking-sync event (the waiting host
-    // thread sleeps instead of spinning)
+    // thread sleeps instead of spinning).  TWO calls may be in flight: each has its own staging buffers and events
+    // (slot = call number & 1), so the uploads of call k+1 run under the kernels of call k and the 4K download of
+    // call k under the kernels of call k+1.
+    struct HostSlot {
+        uint8_t* in_dev; size_t in_bytes;          // staged SBS frames
+        uint8_t* guide_dev; size_t guide_bytes;    // staged guide frames
+        uint16_t* out_dev; size_t out_bytes;       // upscaled output before its download
+        cudaEvent_t ev_sbs, ev_guide, ev_compute, ev_done;
+        int pending;                               // submitted and not waited for yet
+        int used;                                  // ev_compute / ev_done have been recorded at least once
+        unsigned long long call;                   // number of the call that occupies the slot
+    } hs[2];
     cudaStream_t up_stream, down_stream;
-    cudaEvent_t ev_entry, ev_sbs, ev_guide, ev_compute, ev_done;
-    int host_pending;        // an asynchronous host call has not been waited for yet
-    int host_calls;          // asynchronous host calls issued so far
+    cudaEvent_t ev_entry, ev_small;                // caller's stream at entry; the small downloads (disp / f32 / u16) are done
+    unsigned long long host_calls;                 // asynchronous host calls issued so far
     size_t bytes;
     int last_batch;
 

@@ -71,6 +71,9 @@ def lib():
     L.v3d_guided_upscale_host_async.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.c_float, vp, vp]
     L.v3d_host_copy_only_async.argtypes = [vp, vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]
     L.v3d_host_wait.argtypes = [vp]
+    L.v3d_host_wait_oldest.argtypes = [vp]
+    L.v3d_host_pending.argtypes = [vp]
+    L.v3d_host_pending.restype = C.c_int
     L.v3d_fused_sweep_clusters.argtypes = [vp]
     L.v3d_fused_sweep_clusters.restype = i32
     L.v3d_launch_count.argtypes = [vp]
@@ -89,7 +92,7 @@ def lib():
                  "v3d_sgbm_compute", "v3d_set_debug_taps", "v3d_debug_tap", "v3d_debug_tap_copy", "v3d_postprocess", "v3d_normalize_u16",
                  "v3d_guided_upscale", "v3d_depth_frames", "v3d_depth_frames_host", "v3d_set_depth_scale", "v3d_png16_pack", "v3d_set_timing",
                  "v3d_reset_timing", "v3d_depth_frames_host_async", "v3d_guided_upscale_host_async", "v3d_host_copy_only_async",
-                 "v3d_host_wait"):
+                 "v3d_host_wait", "v3d_host_wait_oldest"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -408,5 +411,15 @@ class Context:
                                                   _stream(self.device)), "v3d_host_copy_only_async")
 
     def host_wait(self):
-        """Sleep until the last asynchronous host call of this context has delivered its outputs."""
+        """Sleep until every asynchronous host call of this context has delivered its outputs."""
         _check(lib().v3d_host_wait(self._h), "v3d_host_wait")
+
+    def host_wait_oldest(self):
+        """Sleep until the OLDEST asynchronous host call in flight has delivered its outputs (two may be in flight:
+        submit k+1, then wait for k)."""
+        _check(lib().v3d_host_wait_oldest(self._h), "v3d_host_wait_oldest")
+
+    @property
+    def host_pending(self) -> int:
+        """Asynchronous host calls in flight (0, 1 or 2)."""
+        return int(lib().v3d_host_pending(self._h))
