@@ -199,8 +199,10 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
             const float bp = __uint_as_float(old.y);
             // exact planes (integers): I, I.I
             V[0] += a0 - b0; V[1] += a1 - b1; V[2] += a2 - b2;
-            V[7] += fmaf(a0, a0, -(b0 * b0));  V[8] += fmaf(a0, a1, -(b0 * b1));  V[9] += fmaf(a0, a2, -(b0 * b2));
-            V[10] += fmaf(a1, a1, -(b1 * b1)); V[11] += fmaf(a1, a2, -(b1 * b2)); V[12] += fmaf(a2, a2, -(b2 * b2));
+            // (integers below 2^24 at every intermediate step, so two fused multiply-adds give the same bits as
+            // product difference + add, with one instruction less per plane)
+            V[7] = fmaf(-b0, b0, fmaf(a0, a0, V[7]));   V[8] = fmaf(-b0, b1, fmaf(a0, a1, V[8]));   V[9] = fmaf(-b0, b2, fmaf(a0, a2, V[9]));
+            V[10] = fmaf(-b1, b1, fmaf(a1, a1, V[10])); V[11] = fmaf(-b1, b2, fmaf(a1, a2, V[11])); V[12] = fmaf(-b2, b2, fmaf(a2, a2, V[12]));
             // depth planes: compensated
             kahan(V[3], C[0], ap - bp);
             kahan(V[4], C[1], fmaf(a0, ap, -(b0 * bp)));
@@ -314,10 +316,12 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
                     for (int q = 0; q < 13; q++) acc[q] += m[q];
                 }
 #pragma unroll
+                const float w6 = half ? 0.0f : 1.0f;                    // the upper half has only 6 shared columns
+#pragma unroll
                 for (int t = 0; t < 7; t++) {                           // half of the shared columns: 4..10 / 11..16
                     ld13(4 + t, t < 6 ? 11 + t : 11);
 #pragma unroll
-                    for (int q = 0; q < 13; q++) part[q] += (t == 6 && half) ? 0.0f : m[q];
+                    for (int q = 0; q < 13; q++) part[q] = t < 6 ? part[q] + m[q] : fmaf(m[q], w6, part[q]);   // x * 1 + y rounds like x + y
                 }
 #pragma unroll
                 for (int q = 0; q < 13; q++) acc[q] += part[q] + __shfl_xor_sync(0xffffffffu, part[q], 16);
