@@ -315,7 +315,6 @@ k_guided_coeff_s(const uint16_t* __restrict__ depth, int w, int h, const uint8_t
 #pragma unroll
                     for (int q = 0; q < 13; q++) acc[q] += m[q];
                 }
-#pragma unroll
                 const float w6 = half ? 0.0f : 1.0f;                    // the upper half has only 6 shared columns
 #pragma unroll
                 for (int t = 0; t < 7; t++) {                           // half of the shared columns: 4..10 / 11..16
