@@ -18,8 +18,9 @@
  *     owns only the opaque context and its workspace.
  *   - Every call takes the cudaStream_t to run on (as void*; 0 = legacy default
  *     stream; pass torch.cuda.current_stream().cuda_stream) and is stream-ordered
- *     with no internal synchronisation, except v3d_depth_frames_host and
- *     v3d_host_wait, which wait (sleeping, not spinning) for the outputs.
+ *     with no internal synchronisation, except v3d_depth_frames_host,
+ *     v3d_host_wait and v3d_host_wait_oldest, which wait (sleeping, not spinning)
+ *     for the outputs (so does a third *_host_async call while two are in flight).
  *   - A context belongs to one device and one host thread at a time.
  *   - There is NO CPU fallback: without a CUDA device every compute entry point
  *     fails with V3D_ECUDA.
